@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and ms/frame of the hot path on B200, with the CPU reference beside it.
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): the main.rs scene
+(teapot mesh 6,320 triangles + two 200-triangle mirror disks + dummy = 6,721 `Triangle`s) at
+3840x2160, maxdepth 5, 1 spp, shipped materials (Matte teapot, fuzzy Reflective disks).
+A "step" is one full frame: primary-ray generation, LBVH traversal, exact ray/triangle tests,
+bounce shading and accumulation for all 8,294,400 pixels (~14.26 M rays).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # one JSON line (rank 0)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                            # CPU reference arm (oracle port)
+
+value   : Mrays/s, frame rendered into a device-resident buffer (inputs resident in HBM), CUDA events
+          on the launching stream, max over ranks; rays = project_ray calls with depth>0
+          (the reference's own counter, raytrace.rs:1278), summed over ranks.
+e2e     : same metric through the public API B200RayCaster.walk_rays (-> rtb_render) with HOST
+          buffers: per step the view goes H2D as kernel parameters and the whole W*H*16-byte image
+          comes back D2H into pinned host memory, inside the timed region.  One process drives all N
+          GPUs (the drop-in shape); under torchrun rank 0 does it while the other ranks wait.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, MAXDEPTH, SPP, SEED = 3840, 2160, 5, 1, 7
+WORKLOAD = "teapot 4K multi-bounce (main.rs scene, 6721 tris, 3840x2160, maxdepth 5, 1 spp, shipped materials)"
+FP32_LANES_PER_SM, N_SM = 128, 148
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self, gpu_index=0):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9 or not f[0].isdigit() or int(f[0]) != gpu_index:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference arm (the oracle restatement running the reference's octree algorithm)
+# --------------------------------------------------------------------------------------------
+def cpu_reference(rows, threads=None, repeat=1):
+    """Times the oracle in reference-algorithm mode (octree, row work-queue over host threads) on image
+    rows [rows[0], rows[1]) of the benchmark frame.  Returns (Mrays/s, rays, seconds, cores)."""
+    from oracle import oracle as O
+    import rust_raytrace_b200 as R   # host-side scene construction only (no GPU use)
+    cores = threads or os.cpu_count() or 1
+    scene = R.main_scene(deterministic=False)
+    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE, build_threads=cores)   # build excluded, as main.rs:160 vs :191
+    ov = O.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
+    best = None
+    for _ in range(repeat):
+        _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
+        if best is None or st.seconds < best[2]:
+            best = (st.rays / st.seconds / 1e6, int(st.rays), float(st.seconds), cores)
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    import rust_raytrace_b200 as R   # host-side scene construction only (no GPU use)
+    cores = os.cpu_count() or 1
+    scene = R.main_scene(deterministic=False)
+    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE, build_threads=cores)
+    ov = O.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
+    # bounded sample per step: a band through the middle of the frame (teapot + both disks), sized so that
+    # warmup+steps stay within a few minutes whatever the host: 2 s of work at the rate of a 16-row probe
+    _, _, _, probe = osc.render(ov, seed=SEED, threads=cores, rows=(1072, 1088), want_ids=False)
+    n_rows = int(min(HEIGHT, max(16, 16 * 2.0 / max(probe.seconds, 1e-3)))) // 8 * 8
+    rows = (max(0, 1080 - n_rows // 2), min(HEIGHT, 1080 - n_rows // 2 + n_rows))
+    rates, secs, rays = [], [], 0
+    for i in range(args.warmup + args.steps):
+        _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
+        rays = int(st.rays)
+        if i >= args.warmup:
+            rates.append(st.rays / st.seconds / 1e6); secs.append(st.seconds)
+    value = float(np.mean(rates))
+    frame_rays = 14259831
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3),
+        "ms_per_frame_extrapolated": frame_rays / (value * 1e6) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"rows {rows[0]}..{rows[1]} of {HEIGHT} per step"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                         "sample": f"image rows {rows[0]}..{rows[1]} of the 4K frame, {rays} rays per step, "
+                                   "oracle in reference-algorithm mode (octree 204,894 nodes, row work-queue)"},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import rust_raytrace_b200 as R
+    from rust_raytrace_b200 import _lib
+    L = _lib.lib()
+
+    dev_ids = (C.c_int * 1)(local_rank)
+    _lib.check(L.rtb_init(1, dev_ids), "rtb_init")
+    scene = R.main_scene(deterministic=False)
+    h = scene.upload()
+    info = scene.info()
+    view = R.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
+    view.seed = SEED
+    npix = WIDTH * HEIGHT
+
+    d_rgba = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step(stats=None):
+        _lib.check(L.rtb_render_device(h, C.byref(view), 0, rank, world, d_rgba.data_ptr(), None, None,
+                                       C.c_void_p(stream.cuda_stream), stats), "rtb_render_device")
+
+    # one counted frame: rays and (with the STATS kernel variant) node / triangle tests per ray
+    st = _lib.RtbStats()
+    step(C.byref(st))
+    my_rays = int(st.rays)
+    vstat = _lib.RtbView.from_buffer_copy(view)
+    vstat.flags |= _lib.RTB_FLAG_STATS
+    st2 = _lib.RtbStats()
+    _lib.check(L.rtb_render_device(h, C.byref(vstat), 0, rank, world, d_rgba.data_ptr(), None, None,
+                                   C.c_void_p(stream.cuda_stream), C.byref(st2)), "rtb_render_device(stats)")
+    n_node, n_tri = st2.node_tests / max(st2.rays, 1), st2.tri_tests / max(st2.rays, 1)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(0)              # L2 flush between timed iterations (outside the events)
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop(local_rank) if rank == 0 else None
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_mine = float(np.mean(ms_steps))
+
+    tens = torch.tensor([ms_mine, float(my_rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tens.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tens.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_step, total_rays = float(mx[0]), float(sm[1])
+    else:
+        ms_step, total_rays = ms_mine, float(my_rays)
+    value = total_rays / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e through the public API with host buffers (rank 0 drives all N GPUs) ----
+    e2e = None
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        ids = (C.c_int * args.gpus)(*range(args.gpus))
+        scene.release()
+        _lib.check(L.rtb_init(args.gpus, ids), "rtb_init(all)")
+        sc_all = R.main_scene(deterministic=False)
+        caster = R.B200RayCaster(seed=SEED)
+        caster._n_gpus = args.gpus
+        host = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
+        data = host.numpy()
+        vv = R.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
+        for _ in range(max(args.warmup, 3)):
+            caster.walk_rays(vv, sc_all, data, threads=args.gpus)
+        t0 = time.perf_counter()
+        rays_e2e = 0
+        for _ in range(args.steps):
+            ctx = caster.walk_rays(vv, sc_all, data, threads=args.gpus)
+            rays_e2e += ctx.total_rays
+        dt = time.perf_counter() - t0
+        e2e = {"value": rays_e2e / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / args.steps * 1e3,
+               "h2d_bytes_per_step": C.sizeof(_lib.RtbView), "d2h_bytes_per_step": npix * 16,
+               "api": "B200RayCaster.walk_rays -> rtb_render (pinned host image, scene resident)"}
+        assert int(caster.stats.rays) == int(total_rays), (caster.stats.rays, total_rays)
+        sc_all.release()
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+        rays_per_launch = total_rays / world
+        b_ray = n_node * 32 + n_tri * 80 + 16                      # node 32 B, triangle 80 B, pixel 16 B
+        w_ray = n_node * 24 + n_tri * 54 + 45                      # FP32 lane-ops per ray
+        launch_s = ms_mine * 1e-3
+        ach_gbs = rays_per_launch * b_ray / launch_s / 1e9
+        fp32_peak = N_SM * FP32_LANES_PER_SM * sm_max_mhz * 1e6
+        ach_fp32 = rays_per_launch * w_ray / launch_s
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            mr, rays, s, cores = cpu_reference((1000, 1128))
+            cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                   "sample": f"image rows 1000..1128 of the same 4K frame ({rays} rays, {s:.1f} s), oracle in "
+                             "reference-algorithm mode (octree, row work-queue, all host threads)"}
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_frame": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_frame": int(total_rays), "partition": f"8-row bands, band b -> rank b % {world}",
+                       "l2": "flushed between timed iterations (256 MiB fill); scene (1.3 MB) is re-read from HBM each step",
+                       "bvh": {"nodes": info.n_nodes, "leaves": info.n_leaves, "max_leaf": info.max_leaf,
+                               "height": info.tree_height, "ms_build": info.ms_build, "ms_upload": info.ms_upload},
+                       "node_tests_per_ray": n_node, "tri_tests_per_ray": n_tri, "wall_s_timed_region": t_wall},
+            "gpu_launches": args.steps * 1 * world,
+            "clocks": clocks,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes = rays * (32*N_node + 80*N_tri + 16); the working set is L1/L2 resident, "
+                                 "so this path is bounded by FP32 issue + cache latency, see roofline_fp32"},
+            "roofline_fp32": {"bound": "fp32_issue", "achieved": ach_fp32 / 1e12, "peak": fp32_peak / 1e12,
+                              "unit": "Tlane-op/s", "frac": ach_fp32 / fp32_peak,
+                              "lane_ops_per_ray": w_ray, "kernel": "k_trace"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+/*
+ * rtb.h — C ABI of the B200-native renderer core ("rtb" = ray-trace B200).
+ *
+ * Drop-in boundary behind the reference's `RayCaster` trait
+ * (raytrace_lib/src/raytrace.rs:1128-1165).  A Rust shim
+ * (`B200RayCaster: RayCaster`, see INTEGRATION.md and
+ * rust_raytrace_b200/rust/) converts `Scene.tris` into RtbTriangle[], the
+ * `Viewport` into RtbView, and hands `data: &mut [Color]` (16-byte f32x4
+ * pixels) to rtb_render() as `rgba_out`.
+ *
+ * Replaces, on the reference side:
+ *   - DefaultRayCaster::walk_rays_internal   raytrace.rs:1175-1195
+ *   - Viewport::walk_ray_set / pixel_ray     raytrace.rs:1374-1440
+ *   - project_ray / color_ray                raytrace.rs:1199-1295
+ *   - BoundingBox::get_object_intersection_for_ray (octree) raytrace.rs:910-1050
+ *     -> replaced by a GPU-built LBVH with identical closest-hit semantics
+ *   - the WIP cxx FFI `exec_cuda_raytrace`   cuda_raytrace_lib/src/cuda_rt.h:7-14
+ *
+ * Conventions: plain C, caller owns every host buffer, the library owns device
+ * memory for the lifetime of the scene handle.  Every function returns
+ * RTB_OK (0) or a negative RtbStatus and never aborts; rtb_last_error() gives
+ * a thread-local message.  There is no CPU fallback: without a CUDA device
+ * every entry point that needs one fails with RTB_ERR_NO_DEVICE.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_VERSION 1
+#define RTB_MAX_DEPTH 16   /* Viewport.maxdepth above this is rejected (reference uses 5, main.rs:172) */
+#define RTB_MAX_GPUS 8
+
+typedef enum RtbStatus {
+    RTB_OK = 0,
+    RTB_ERR_NO_DEVICE = -1,
+    RTB_ERR_CUDA = -2,
+    RTB_ERR_INVALID = -3,
+    RTB_ERR_NOMEM = -4
+} RtbStatus;
+
+/* SurfaceKind discriminants, raytrace.rs:303-308. */
+enum { RTB_SOLID = 0, RTB_MATTE = 1, RTB_REFLECTIVE = 2 };
+
+/* One `Triangle` (raytrace.rs:326-337) in the reference's field order, flattened
+ * to 35 4-byte fields (140 B).  `surface` is flattened to kind/color/alpha/scattering
+ * (Solid uses color only; Matte color+alpha; Reflective all three).  `num` is the
+ * array index (populate_triangle_numbers, raytrace.rs:393-397) and is implicit.
+ * Index 0 is the reference's dummy triangle: never tested, prim id 0 = miss. */
+typedef struct RtbTriangle {
+    float incenter[3];
+    float norm[3];
+    float bounding_r2;
+    float sides[9];
+    float side_lens[3];
+    float corners[9];
+    float edge_thickness;
+    uint32_t kind;
+    float color[3];
+    float alpha;
+    float scattering;
+} RtbTriangle;
+
+/* `Viewport` (raytrace.rs:1305-1318) plus the render controls the reference
+ * hard-codes.  orig/cam/vu/vv are the private fields computed by
+ * create_viewport (raytrace.rs:1343-1370). */
+typedef struct RtbView {
+    uint32_t width, height;
+    float orig[3];
+    float cam[3];
+    float vu[3];
+    float vv[3];
+    uint32_t maxdepth;        /* >= 1, <= RTB_MAX_DEPTH */
+    uint32_t spp;             /* samples_per_pixel; 1 => pixel centre, no jitter (raytrace.rs:1382) */
+    uint64_t seed;            /* counter-based RNG seed (the reference's ThreadRng is unseeded) */
+    uint32_t sample_begin;    /* progressive / multi-GPU sample partition: samples        */
+    uint32_t sample_end;      /*   [sample_begin, sample_end) of spp; 0,0 => all           */
+    uint32_t flags;           /* RTB_FLAG_* */
+    uint32_t reserved;
+} RtbView;
+
+enum {
+    RTB_FLAG_SUM_ONLY = 1u,   /* write the un-normalised sample sum (for a later cross-GPU reduce) */
+    RTB_FLAG_STATS    = 2u,   /* also count node/triangle tests (slower kernel variant)            */
+    RTB_FLAG_BRUTE    = 4u    /* validation: ignore the BVH, test every primitive (the GPU analogue of
+                                 build_trivial_bounding_box, raytrace.rs:847-856)                  */
+};
+
+typedef struct RtbStats {
+    uint64_t rays;            /* project_ray calls with depth>0 — the reference's "Rays" (raytrace.rs:1278) */
+    uint64_t node_tests;      /* AABB slab tests   (RTB_FLAG_STATS only) */
+    uint64_t tri_tests;       /* exact triangle tests (RTB_FLAG_STATS only) */
+    double   ms_render;       /* device time of the trace kernels, max over GPUs (CUDA events) */
+    double   ms_total;        /* host wall time of the call incl. copies */
+    uint32_t kernel_launches; /* kernels launched by this call */
+    uint32_t n_gpus;
+} RtbStats;
+
+typedef struct RtbSceneInfo {
+    uint32_t n_tris;          /* triangles passed in (incl. the dummy at 0) */
+    uint32_t n_prims;         /* triangles in the BVH after the root-cube cull */
+    uint32_t n_nodes;         /* 32-byte BVH nodes */
+    uint32_t n_leaves;
+    uint32_t max_leaf;
+    uint32_t tree_height;
+    float    scene_lo[3], scene_hi[3];
+    double   ms_upload;       /* H2D + SoA repack */
+    double   ms_build;        /* LBVH build (morton, sort, hierarchy, refit, emit), device time */
+    uint32_t build_launches;
+    uint32_t n_gpus;
+} RtbSceneInfo;
+
+typedef struct rtb_scene rtb_scene;
+
+/* Select the devices this process drives.  n_gpus = 0 -> all visible devices;
+ * device_ids NULL -> 0..n_gpus-1.  Idempotent; re-initialising with a different
+ * set is allowed when no scene is alive. */
+int rtb_init(int n_gpus, const int* device_ids);
+int rtb_device_count(void);          /* devices selected by rtb_init, or <0 */
+void rtb_shutdown(void);
+const char* rtb_last_error(void);
+
+/* Upload `n` triangles, repack to the device layout and build the LBVH on every
+ * selected GPU.  root_orig/root_len2: the reference's octree root cube
+ * (build_bounding_box args, main.rs:160-164); triangles for which
+ * box_contains_polygon(root) (raytrace.rs:753-779) is false are invisible in
+ * the reference and are culled here too.  root_len2 <= 0 disables the cull. */
+int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
+                     rtb_scene** out);
+int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* out);
+void rtb_scene_destroy(rtb_scene* s);
+/* Debug/inspection: copy the BVH of GPU 0 back (nodes: n_nodes*8 floats; prim_order: n_prims u32
+ * = original triangle index of each leaf-order slot).  Either pointer may be NULL. */
+int rtb_scene_download_bvh(const rtb_scene* s, float* nodes, uint32_t* prim_order);
+
+/* Render one frame into HOST buffers (the RayCaster::walk_rays_internal replacement).
+ *   rgba_out : width*height*4 f32, row-major `row*width+col`, lane 3 = 0 — may be the Rust `&mut [Color]`.
+ *   prim_out : nullable, width*height u32 — primitive id of the primary ray of sample 0, 0 = miss.
+ *   t_out    : nullable, width*height f32 — its hit time (0 on miss).
+ * Work is split over the selected GPUs in interleaved 16x8-pixel tiles; every GPU copies its own
+ * tiles back over its own PCIe link.  Pin the buffers with rtb_host_register for full D2H speed. */
+int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* prim_out, float* t_out,
+               RtbStats* stats);
+
+/* Render the tile subset `tile_rank` of `tile_world` (tile i belongs to rank i % world) of one frame
+ * into DEVICE buffers (full-frame indexing, pixels of other ranks untouched) on GPU slot `gpu`
+ * (index into the rtb_init set) and CUDA stream `stream` (a cudaStream_t cast to void*, NULL = the
+ * library's stream).  Asynchronous when stats == NULL.  Used by bench.py's resident-input timing and
+ * by the one-process-per-GPU launch (torchrun), where the caller owns the buffers. */
+int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_rank, uint32_t tile_world,
+                      float* d_rgba, uint32_t* d_prim, float* d_t, void* stream, RtbStats* stats);
+
+/* Multi-sample frame with the SAMPLES partitioned over the selected GPUs (sample s -> GPU s % n),
+ * per-GPU f32 sum buffers combined over NVLink peer memory: every GPU reduces and normalises one
+ * horizontal band reading its peers' buffers directly, then copies the band to rgba_out.  */
+int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, RtbStats* stats);
+
+/* (c*255.) as u8 quantiser of write_png (raytrace.rs:1468-1473) on the GPU: rgba f32 host -> rgb8 host. */
+int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out);
+
+/* Which image rows does `rank` of `world` render?  (Band partition: 8-row band b belongs to rank
+ * b % world.)  Writes up to `cap` row indices in ascending order, returns the number of rows owned.
+ * Host-only; needs no GPU. */
+int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t* rows_out, uint32_t cap);
+
+/* Pin / unpin a caller-owned host buffer (cudaHostRegister) so D2H runs at PCIe speed. */
+int rtb_host_register(void* ptr, size_t bytes);
+int rtb_host_unregister(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */

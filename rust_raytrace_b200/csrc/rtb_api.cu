@@ -1,0 +1,473 @@
+// rtb_api.cu — the C ABI of include/rtb.h: device selection, scene upload + LBVH build,
+// frame rendering into host or device buffers, progressive multi-GPU rendering.
+#include <chrono>
+#include <cstring>
+#include <mutex>
+
+#include "rtb_internal.cuh"
+#include "host/raytrace_host.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+std::vector<int> g_devices;   // devices selected by rtb_init
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+void rtb_set_error(const std::string& msg) { g_err = msg; }
+
+int rtb_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    g_err = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") in " + what + " at " +
+            file + ":" + std::to_string(line);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RTB_ERR_NO_DEVICE
+           : (e == cudaErrorMemoryAllocation)                            ? RTB_ERR_NOMEM
+                                                                          : RTB_ERR_CUDA;
+}
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int ensure_init() {
+    if (!g_devices.empty()) return RTB_OK;
+    return rtb_init(1, nullptr);
+}
+
+void free_gpu_scene(GpuScene& g) {
+    if (g.device < 0) return;
+    cudaSetDevice(g.device);
+    if (g.stream) cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_nodes); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
+    cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t);
+    if (g.ev0) cudaEventDestroy(g.ev0);
+    if (g.ev1) cudaEventDestroy(g.ev1);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g = GpuScene();
+}
+
+int ensure_framebuffer(GpuScene& g, size_t pixels, bool want_prim, bool want_t) {
+    if (g.fb_pixels < pixels) {
+        cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t);
+        g.d_rgba = nullptr; g.d_prim = nullptr; g.d_t = nullptr; g.fb_pixels = 0;
+        RTB_CUDA(cudaMalloc(&g.d_rgba, pixels * sizeof(float4)));
+        g.fb_pixels = pixels;
+    }
+    if (want_prim && !g.d_prim) RTB_CUDA(cudaMalloc(&g.d_prim, g.fb_pixels * sizeof(uint32_t)));
+    if (want_t && !g.d_t) RTB_CUDA(cudaMalloc(&g.d_t, g.fb_pixels * sizeof(float)));
+    return RTB_OK;
+}
+
+int check_view(const RtbView* v) {
+    if (!v) return fail(RTB_ERR_INVALID, "view is NULL");
+    if (v->width == 0 || v->height == 0) return fail(RTB_ERR_INVALID, "viewport has zero width or height");
+    if (v->maxdepth > RTB_MAX_DEPTH)
+        return fail(RTB_ERR_INVALID, "maxdepth " + std::to_string(v->maxdepth) + " exceeds RTB_MAX_DEPTH");
+    if (v->spp == 0) return fail(RTB_ERR_INVALID, "samples_per_pixel must be >= 1");
+    if (v->sample_end > v->spp || v->sample_begin > v->sample_end)
+        return fail(RTB_ERR_INVALID, "sample range outside [0, spp]");
+    return RTB_OK;
+}
+
+ViewDev make_view(const RtbView& v, uint32_t rank, uint32_t world, bool compact) {
+    ViewDev d;
+    std::memset(&d, 0, sizeof d);
+    d.width = v.width; d.height = v.height;
+    for (int k = 0; k < 3; ++k) { d.orig[k] = v.orig[k]; d.cam[k] = v.cam[k]; d.vu[k] = v.vu[k]; d.vv[k] = v.vv[k]; }
+    d.maxdepth = v.maxdepth; d.spp = v.spp; d.seed = v.seed;
+    d.s_begin = v.sample_begin; d.s_end = v.sample_end;
+    if (d.s_begin == 0 && d.s_end == 0) d.s_end = v.spp;
+    d.flags = v.flags;
+    d.tile_rank = rank; d.tile_world = world;
+    d.tiles_x = (v.width + RTB_TILE_W - 1) / RTB_TILE_W;
+    const uint32_t tiles_y = (v.height + RTB_TILE_H - 1) / RTB_TILE_H;
+    d.my_tile_rows = tiles_y > rank ? (tiles_y - rank + world - 1) / world : 0;
+    d.compact = compact ? 1u : 0u;
+    return d;
+}
+
+SceneDev scene_dev(const GpuScene& g, uint32_t n_prims) {
+    SceneDev s;
+    s.nodes = g.d_nodes; s.tri = g.d_tri; s.shade = g.d_shade; s.n_prims = n_prims; s.n_nodes = g.n_nodes;
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtb_last_error(void) { return g_err.c_str(); }
+
+int rtb_init(int n_gpus, const int* device_ids) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(RTB_ERR_NO_DEVICE, std::string("no CUDA device available (") +
+                                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                           "); this library has no CPU fallback");
+    }
+    if (n_gpus <= 0) n_gpus = count;
+    if (n_gpus > RTB_MAX_GPUS) return fail(RTB_ERR_INVALID, "more than RTB_MAX_GPUS devices requested");
+    std::vector<int> devs;
+    for (int i = 0; i < n_gpus; ++i) {
+        int d = device_ids ? device_ids[i] : i;
+        if (d < 0 || d >= count) return fail(RTB_ERR_INVALID, "device id " + std::to_string(d) + " out of range");
+        devs.push_back(d);
+    }
+    // peer access between every pair (needed by rtb_render_progressive; harmless otherwise)
+    for (size_t a = 0; a < devs.size(); ++a)
+        for (size_t b = 0; b < devs.size(); ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
+            if (can) {
+                cudaSetDevice(devs[a]);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b], 0);
+                if (pe != cudaSuccess) cudaGetLastError();   // already enabled is fine
+            }
+        }
+    RTB_CUDA(cudaSetDevice(devs[0]));
+    g_devices = devs;
+    return RTB_OK;
+}
+
+int rtb_device_count(void) { return g_devices.empty() ? RTB_ERR_INVALID : (int)g_devices.size(); }
+
+void rtb_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_devices.clear();
+}
+
+int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
+                     rtb_scene** out) {
+    if (!out) return fail(RTB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n > 0 && !tris) return fail(RTB_ERR_INVALID, "tris is NULL");
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+
+    // Root-cube cull (raytrace.rs:795-805): triangle 0 is never in the tree (:791).
+    std::vector<uint32_t> keep;
+    keep.reserve(n);
+    for (uint32_t i = 1; i < n; ++i) {
+        if (root_len2 > 0.f && root_orig) {
+            const raytrace::Point c = raytrace::make_vec(root_orig[0], root_orig[1], root_orig[2]);
+            if (!raytrace::box_contains_polygon(c, root_len2, tris[i])) continue;
+        }
+        keep.push_back(i);
+    }
+    const uint32_t n_prims = (uint32_t)keep.size();
+
+    rtb_scene* s = new rtb_scene();
+    std::memset(&s->info, 0, sizeof s->info);
+    s->info.n_tris = n;
+    s->info.n_prims = n_prims;
+    s->info.n_gpus = (uint32_t)g_devices.size();
+    s->gpu.resize(g_devices.size());
+
+    for (size_t gi = 0; gi < g_devices.size(); ++gi) {
+        GpuScene& g = s->gpu[gi];
+        g.device = g_devices[gi];
+        auto bail = [&](int code) { for (auto& x : s->gpu) free_gpu_scene(x); delete s; return code; };
+        cudaError_t e;
+        if ((e = cudaSetDevice(g.device)) != cudaSuccess) return bail(rtb_cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__));
+        if ((e = cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(rtb_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+        cudaEventCreate(&g.ev0);
+        cudaEventCreate(&g.ev1);
+        if ((e = cudaMalloc(&g.d_counters, sizeof(TraceCounters))) != cudaSuccess)
+            return bail(rtb_cuda_fail(e, "cudaMalloc(counters)", __FILE__, __LINE__));
+
+        const double t0 = now_ms();
+        RtbTriangle* d_tris = nullptr;
+        uint32_t* d_keep = nullptr;
+        if ((e = cudaMalloc(&d_tris, sizeof(RtbTriangle) * (n ? n : 1))) != cudaSuccess)
+            return bail(rtb_cuda_fail(e, "cudaMalloc(tris)", __FILE__, __LINE__));
+        if ((e = cudaMalloc(&d_keep, sizeof(uint32_t) * (n_prims ? n_prims : 1))) != cudaSuccess) {
+            cudaFree(d_tris);
+            return bail(rtb_cuda_fail(e, "cudaMalloc(keep)", __FILE__, __LINE__));
+        }
+        cudaMemcpyAsync(d_tris, tris, sizeof(RtbTriangle) * n, cudaMemcpyHostToDevice, g.stream);
+        cudaMemcpyAsync(d_keep, keep.data(), sizeof(uint32_t) * n_prims, cudaMemcpyHostToDevice, g.stream);
+        cudaStreamSynchronize(g.stream);
+        const double t1 = now_ms();
+
+        BuildResult br;
+        rc = rtb_build_lbvh(d_tris, d_keep, n_prims, g.stream, &br);
+        cudaFree(d_tris);
+        cudaFree(d_keep);
+        g.d_nodes = br.d_nodes; g.d_tri = br.d_tri; g.d_shade = br.d_shade; g.d_prim_order = br.d_prim_order;
+        g.n_nodes = br.n_nodes;
+        if (rc != RTB_OK) return bail(rc);
+        if (gi == 0) {
+            s->info.n_nodes = br.n_nodes; s->info.n_leaves = br.n_leaves; s->info.max_leaf = br.max_leaf;
+            s->info.tree_height = br.tree_height;
+            for (int k = 0; k < 3; ++k) { s->info.scene_lo[k] = br.lo[k]; s->info.scene_hi[k] = br.hi[k]; }
+            s->info.build_launches = br.launches;
+        }
+        s->info.ms_upload = std::max(s->info.ms_upload, t1 - t0);
+        s->info.ms_build = std::max(s->info.ms_build, (double)br.ms_build);
+    }
+    *out = s;
+    return RTB_OK;
+}
+
+int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* out) {
+    if (!s || !out) return fail(RTB_ERR_INVALID, "NULL argument");
+    *out = s->info;
+    return RTB_OK;
+}
+
+void rtb_scene_destroy(rtb_scene* s) {
+    if (!s) return;
+    for (auto& g : s->gpu) free_gpu_scene(g);
+    delete s;
+}
+
+int rtb_scene_download_bvh(const rtb_scene* s, float* nodes, uint32_t* prim_order) {
+    if (!s) return fail(RTB_ERR_INVALID, "scene is NULL");
+    const GpuScene& g = s->gpu[0];
+    RTB_CUDA(cudaSetDevice(g.device));
+    if (nodes) RTB_CUDA(cudaMemcpy(nodes, g.d_nodes, sizeof(float4) * 2 * g.n_nodes, cudaMemcpyDeviceToHost));
+    if (prim_order && s->info.n_prims)
+        RTB_CUDA(cudaMemcpy(prim_order, g.d_prim_order, sizeof(uint32_t) * s->info.n_prims, cudaMemcpyDeviceToHost));
+    return RTB_OK;
+}
+
+int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_rank, uint32_t tile_world,
+                      float* d_rgba, uint32_t* d_prim, float* d_t, void* stream, RtbStats* stats) {
+    if (!s) return fail(RTB_ERR_INVALID, "scene is NULL");
+    int rc = check_view(view);
+    if (rc != RTB_OK) return rc;
+    if (gpu < 0 || gpu >= (int)s->gpu.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
+    if (tile_world == 0 || tile_rank >= tile_world) return fail(RTB_ERR_INVALID, "bad tile_rank/tile_world");
+    if (!d_rgba) return fail(RTB_ERR_INVALID, "d_rgba is NULL");
+    GpuScene& g = s->gpu[gpu];
+    RTB_CUDA(cudaSetDevice(g.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+    const ViewDev vd = make_view(*view, tile_rank, tile_world, false);
+    const double t0 = now_ms();
+    uint32_t launches = 0;
+    if (stats) {
+        RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), st));
+        RTB_CUDA(cudaEventRecord(g.ev0, st));
+    }
+    rc = rtb_launch_trace(scene_dev(g, s->info.n_prims), vd, (float4*)d_rgba, d_prim, d_t, g.d_counters, st, &launches);
+    if (rc != RTB_OK) return rc;
+    if (stats) {
+        RTB_CUDA(cudaEventRecord(g.ev1, st));
+        TraceCounters c;
+        RTB_CUDA(cudaMemcpyAsync(&c, g.d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+        RTB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        std::memset(stats, 0, sizeof *stats);
+        stats->rays = c.rays; stats->node_tests = c.node_tests; stats->tri_tests = c.tri_tests;
+        stats->ms_render = ms; stats->ms_total = now_ms() - t0; stats->kernel_launches = launches; stats->n_gpus = 1;
+    }
+    return RTB_OK;
+}
+
+int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* prim_out, float* t_out,
+               RtbStats* stats) {
+    if (!s) return fail(RTB_ERR_INVALID, "scene is NULL");
+    int rc = check_view(view);
+    if (rc != RTB_OK) return rc;
+    if (!rgba_out) return fail(RTB_ERR_INVALID, "rgba_out is NULL");
+    const double t0 = now_ms();
+    const uint32_t world = (uint32_t)s->gpu.size();
+    const uint32_t W = view->width, H = view->height;
+    const uint32_t tiles_y = (H + RTB_TILE_H - 1) / RTB_TILE_H;
+    uint32_t launches = 0;
+
+    // phase 1: launch every GPU's bands and its strided copy back, all asynchronous
+    for (uint32_t r = 0; r < world; ++r) {
+        GpuScene& g = s->gpu[r];
+        RTB_CUDA(cudaSetDevice(g.device));
+        const ViewDev vd = make_view(*view, r, world, true);
+        if (vd.my_tile_rows == 0) continue;
+        const size_t pixels = (size_t)vd.my_tile_rows * RTB_TILE_H * W;
+        rc = ensure_framebuffer(g, pixels, prim_out != nullptr, t_out != nullptr);
+        if (rc != RTB_OK) return rc;
+        RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), g.stream));
+        RTB_CUDA(cudaEventRecord(g.ev0, g.stream));
+        rc = rtb_launch_trace(scene_dev(g, s->info.n_prims), vd, g.d_rgba, prim_out ? g.d_prim : nullptr,
+                              t_out ? g.d_t : nullptr, g.d_counters, g.stream, &launches);
+        if (rc != RTB_OK) return rc;
+        RTB_CUDA(cudaEventRecord(g.ev1, g.stream));
+        // band b of this rank = image rows [(b*world + r)*8, +8): one strided copy for all full bands,
+        // one more for a ragged last band.
+        const uint32_t last_ty = (vd.my_tile_rows - 1) * world + r;
+        const bool ragged = (last_ty == tiles_y - 1) && (H % RTB_TILE_H != 0);
+        const uint32_t full_bands = ragged ? vd.my_tile_rows - 1 : vd.my_tile_rows;
+        auto copy_plane = [&](void* host, const void* dev, size_t px_bytes) -> int {
+            const size_t band_bytes = (size_t)RTB_TILE_H * W * px_bytes;
+            char* dst0 = (char*)host + (size_t)r * band_bytes;
+            if (full_bands)
+                RTB_CUDA(cudaMemcpy2DAsync(dst0, band_bytes * world, dev, band_bytes, band_bytes, full_bands,
+                                           cudaMemcpyDeviceToHost, g.stream));
+            if (ragged) {
+                const size_t rows = H - (size_t)last_ty * RTB_TILE_H;
+                RTB_CUDA(cudaMemcpyAsync((char*)host + (size_t)last_ty * band_bytes,
+                                         (const char*)dev + (size_t)full_bands * band_bytes, rows * W * px_bytes,
+                                         cudaMemcpyDeviceToHost, g.stream));
+            }
+            return RTB_OK;
+        };
+        if ((rc = copy_plane(rgba_out, g.d_rgba, sizeof(float4))) != RTB_OK) return rc;
+        if (prim_out && (rc = copy_plane(prim_out, g.d_prim, sizeof(uint32_t))) != RTB_OK) return rc;
+        if (t_out && (rc = copy_plane(t_out, g.d_t, sizeof(float))) != RTB_OK) return rc;
+    }
+    // phase 2: wait and gather stats
+    RtbStats st;
+    std::memset(&st, 0, sizeof st);
+    for (uint32_t r = 0; r < world; ++r) {
+        GpuScene& g = s->gpu[r];
+        RTB_CUDA(cudaSetDevice(g.device));
+        RTB_CUDA(cudaStreamSynchronize(g.stream));
+        const ViewDev vd = make_view(*view, r, world, true);
+        if (vd.my_tile_rows == 0) continue;
+        TraceCounters c;
+        RTB_CUDA(cudaMemcpy(&c, g.d_counters, sizeof c, cudaMemcpyDeviceToHost));
+        float ms = 0.f;
+        RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
+        st.ms_render = std::max(st.ms_render, (double)ms);
+    }
+    st.ms_total = now_ms() - t0;
+    st.kernel_launches = launches;
+    st.n_gpus = world;
+    if (stats) *stats = st;
+    return RTB_OK;
+}
+
+int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, RtbStats* stats) {
+    if (!s) return fail(RTB_ERR_INVALID, "scene is NULL");
+    int rc = check_view(view);
+    if (rc != RTB_OK) return rc;
+    if (!rgba_out) return fail(RTB_ERR_INVALID, "rgba_out is NULL");
+    const double t0 = now_ms();
+    const uint32_t world = (uint32_t)s->gpu.size();
+    const uint32_t W = view->width, H = view->height;
+    const size_t pixels = (size_t)W * H;
+    const uint32_t s_lo = view->sample_begin, s_hi = (view->sample_begin == 0 && view->sample_end == 0) ? view->spp : view->sample_end;
+    const uint32_t n_s = s_hi - s_lo;
+    uint32_t launches = 0;
+
+    // phase 1: every GPU accumulates its contiguous share of the samples over the FULL frame (sum only)
+    std::vector<const float4*> bufs(world);
+    for (uint32_t r = 0; r < world; ++r) {
+        GpuScene& g = s->gpu[r];
+        RTB_CUDA(cudaSetDevice(g.device));
+        rc = ensure_framebuffer(g, 2 * pixels, false, false);   // [0,pixels) = sum buffer, [pixels,2*pixels) = reduced band
+        if (rc != RTB_OK) return rc;
+        bufs[r] = g.d_rgba;
+        RtbView v = *view;
+        v.sample_begin = s_lo + (uint32_t)(((uint64_t)n_s * r) / world);
+        v.sample_end = s_lo + (uint32_t)(((uint64_t)n_s * (r + 1)) / world);
+        v.flags |= RTB_FLAG_SUM_ONLY;
+        RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), g.stream));
+        RTB_CUDA(cudaEventRecord(g.ev0, g.stream));
+        if (v.sample_begin == v.sample_end) {
+            RTB_CUDA(cudaMemsetAsync(g.d_rgba, 0, pixels * sizeof(float4), g.stream));
+        } else {
+            ViewDev vd = make_view(v, 0, 1, false);
+            rc = rtb_launch_trace(scene_dev(g, s->info.n_prims), vd, g.d_rgba, nullptr, nullptr, g.d_counters, g.stream,
+                                  &launches);
+            if (rc != RTB_OK) return rc;
+        }
+        RTB_CUDA(cudaEventRecord(g.ev1, g.stream));
+    }
+    for (uint32_t r = 0; r < world; ++r) {
+        RTB_CUDA(cudaSetDevice(s->gpu[r].device));
+        RTB_CUDA(cudaStreamSynchronize(s->gpu[r].stream));
+    }
+    // phase 2: GPU r reduces pixel range r over NVLink peer loads, normalises and copies it home
+    const float inv_spp = 1.0f / (float)n_s;
+    for (uint32_t r = 0; r < world; ++r) {
+        GpuScene& g = s->gpu[r];
+        RTB_CUDA(cudaSetDevice(g.device));
+        const uint64_t first = (uint64_t)pixels * r / world, last = (uint64_t)pixels * (r + 1) / world;
+        const float4** d_ptrs = nullptr;
+        RTB_CUDA(cudaMalloc(&d_ptrs, sizeof(float4*) * world));
+        RTB_CUDA(cudaMemcpyAsync(d_ptrs, bufs.data(), sizeof(float4*) * world, cudaMemcpyHostToDevice, g.stream));
+        float4* d_out = g.d_rgba + pixels;
+        rc = rtb_launch_peer_reduce(d_ptrs, (int)world, inv_spp, first, last - first, d_out, g.stream);
+        ++launches;
+        if (rc != RTB_OK) { cudaFree(d_ptrs); return rc; }
+        RTB_CUDA(cudaMemcpyAsync(rgba_out + 4 * first, d_out + first, (last - first) * sizeof(float4),
+                                 cudaMemcpyDeviceToHost, g.stream));
+        RTB_CUDA(cudaStreamSynchronize(g.stream));
+        cudaFree(d_ptrs);
+    }
+    RtbStats st;
+    std::memset(&st, 0, sizeof st);
+    for (uint32_t r = 0; r < world; ++r) {
+        GpuScene& g = s->gpu[r];
+        RTB_CUDA(cudaSetDevice(g.device));
+        TraceCounters c;
+        RTB_CUDA(cudaMemcpy(&c, g.d_counters, sizeof c, cudaMemcpyDeviceToHost));
+        float ms = 0.f;
+        RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
+        st.ms_render = std::max(st.ms_render, (double)ms);
+    }
+    st.ms_total = now_ms() - t0;
+    st.kernel_launches = launches;
+    st.n_gpus = world;
+    if (stats) *stats = st;
+    return RTB_OK;
+}
+
+int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out) {
+    if (!rgba || !rgb_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(g_devices[0]));
+    float4* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    RTB_CUDA(cudaMalloc(&d_in, npix * sizeof(float4) + 16));
+    if (cudaMalloc(&d_out, npix * 3 + 16) != cudaSuccess) { cudaFree(d_in); return fail(RTB_ERR_NOMEM, "cudaMalloc"); }
+    cudaMemcpy(d_in, rgba, npix * sizeof(float4), cudaMemcpyHostToDevice);
+    rc = rtb_launch_quantize(d_in, npix, d_out, 0);
+    cudaError_t e = cudaMemcpy(rgb_out, d_out, npix * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (rc != RTB_OK) return rc;
+    if (e != cudaSuccess) return rtb_cuda_fail(e, "cudaMemcpy", __FILE__, __LINE__);
+    return RTB_OK;
+}
+
+int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t* rows_out, uint32_t cap) {
+    if (world == 0 || rank >= world) return fail(RTB_ERR_INVALID, "bad rank/world");
+    uint32_t n = 0;
+    for (uint32_t row = 0; row < height; ++row) {
+        if ((row / RTB_TILE_H) % world != rank) continue;
+        if (rows_out && n < cap) rows_out[n] = row;
+        ++n;
+    }
+    return (int)n;
+}
+
+int rtb_host_register(void* ptr, size_t bytes) {
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return RTB_OK;
+}
+
+int rtb_host_unregister(void* ptr) {
+    RTB_CUDA(cudaHostUnregister(ptr));
+    return RTB_OK;
+}
+
+}  // extern "C"

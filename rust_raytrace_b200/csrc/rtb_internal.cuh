@@ -1,0 +1,123 @@
+// rtb_internal.cuh — shared declarations of the CUDA library (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "rtb.h"
+
+// ---------------------------------------------------------------------------
+// Device-side scene layout (all arrays in HBM, L2-resident for the scenes of
+// interest; see DESIGN.md "Data layout").
+//
+//  nodes : 2 x float4 per BVH2 node (32 bytes):
+//            n0 = (lo.x, lo.y, lo.z, bits(a))     n1 = (hi.x, hi.y, hi.z, bits(b))
+//          internal: a = index of the left child, the right child is a+1 (sibling
+//                    pairs are adjacent and 64-byte aligned), b = 0
+//          leaf    : a = first primitive slot, b = primitive count (> 0)
+//          node 0 is the root, node 1 is padding, pairs start at node 2.
+//  tri   : 5 x float4 per primitive (80 bytes) in leaf order — the 19 floats
+//          Triangle::intersects reads (raytrace.rs:400-422) plus the original index:
+//            q0 = (norm.xyz, bounding_r2)   q1 = (incenter.xyz, bits(orig_index))
+//            q2 = (sides[0].xyz, side_lens[0])  q3, q4 likewise
+//  shade : 2 x float4 per primitive in leaf order, read once per hit:
+//            s0 = (color.rgb, alpha)
+//            s1 = (bits(kind), scattering, edge_thickness, 0)
+// ---------------------------------------------------------------------------
+struct SceneDev {
+    const float4* nodes;
+    const float4* tri;
+    const float4* shade;
+    uint32_t n_prims;
+    uint32_t n_nodes;
+};
+
+#define RTB_TRI_F4 5
+#define RTB_SHADE_F4 2
+#define RTB_LEAF_MAX 4
+#define RTB_STACK 64
+
+// Image tiling: one CTA = 128 threads = 16 x 8 pixels; one warp = 8 x 4 pixels.
+#define RTB_TILE_W 16
+#define RTB_TILE_H 8
+
+struct ViewDev {
+    uint32_t width, height;
+    float orig[3], cam[3], vu[3], vv[3];
+    uint32_t maxdepth, spp;
+    uint64_t seed;
+    uint32_t s_begin, s_end;
+    uint32_t flags;
+    // band partition: tile row ty belongs to rank ty % world
+    uint32_t tile_rank, tile_world;
+    uint32_t tiles_x;        // ceil(width / 16)
+    uint32_t my_tile_rows;   // number of tile rows owned by this rank
+    uint32_t compact;        // 1: output rows are packed (own bands only), 0: full-frame indexing
+};
+
+struct TraceCounters {
+    unsigned long long rays;
+    unsigned long long node_tests;
+    unsigned long long tri_tests;
+};
+
+// Per-GPU state of a scene.
+struct GpuScene {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float4* d_nodes = nullptr;
+    float4* d_tri = nullptr;
+    float4* d_shade = nullptr;
+    uint32_t* d_prim_order = nullptr;  // leaf slot -> original triangle index
+    TraceCounters* d_counters = nullptr;
+    // frame buffers for rtb_render (host-output mode), grown on demand
+    float4* d_rgba = nullptr;
+    uint32_t* d_prim = nullptr;
+    float* d_t = nullptr;
+    size_t fb_pixels = 0;
+    uint32_t n_nodes = 0;
+};
+
+struct rtb_scene {
+    std::vector<GpuScene> gpu;
+    RtbSceneInfo info;
+};
+
+// ---- error plumbing ---------------------------------------------------------
+void rtb_set_error(const std::string& msg);
+int rtb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define RTB_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return rtb_cuda_fail(e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- implemented in rtb_lbvh.cu ---------------------------------------------
+struct BuildResult {
+    float4* d_nodes = nullptr;
+    float4* d_tri = nullptr;
+    float4* d_shade = nullptr;
+    uint32_t* d_prim_order = nullptr;
+    uint32_t n_nodes = 0, n_leaves = 0, max_leaf = 0, tree_height = 0;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    float ms_build = 0.f;
+    uint32_t launches = 0;
+};
+// d_tris: the caller's RtbTriangle array on the device; d_keep: original indices of the n_prims kept triangles.
+int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n_prims, cudaStream_t stream,
+                   BuildResult* out);
+
+// ---- implemented in rtb_trace.cu ----------------------------------------------
+// Launches the trace kernel for the tile rows owned by (tile_rank, tile_world).
+int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint32_t* d_prim, float* d_t,
+                     TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches);
+int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream);
+// Fused cross-GPU reduce of per-GPU sample sums over peer memory: out[i] = (sum_g bufs[g][i]) * inv_spp for
+// pixels [first, first+count).
+int rtb_launch_peer_reduce(const float4* const* d_bufs_on_device, int n_bufs, float inv_spp, uint64_t first,
+                           uint64_t count, float4* d_out, cudaStream_t stream);

@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path (through the C ABI, librtb.so) against the CPU oracle.
+
+Bar (BASELINE.json north_star): hit mask, primitive ids and hit times BIT-EXACT; RGB within 1/255 on
+>= 99.9 % of pixels in the deterministic mode (we assert the stronger bit-exact RGBA), PSNR >= 40 dB
+in the stochastic mode.  Because the oracle and the CUDA path share one counter-based RNG spec,
+stochastic materials are ALSO compared bit for bit; the PSNR test covers the case where the
+summation order legitimately differs (samples partitioned over GPUs).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def gpu_render(R, scene, v, seed=0, want_ids=True, threads=1, stats=False):
+    data = R.new_image(v)
+    caster = R.B200RayCaster(want_ids=want_ids, seed=seed, stats=stats)
+    ctx = caster.walk_rays(v, scene, data, threads=threads, show_progress=False)
+    return data, caster.prim, caster.t, ctx, caster
+
+
+def assert_bit_exact(gpu, ora, what=""):
+    data, prim, t, ctx, _ = gpu
+    rgba, oprim, ot, st = ora
+    bad = int((prim != oprim).sum())
+    assert bad == 0, f"{what}: {bad} primitive ids differ, first at {np.argwhere(prim != oprim)[:5].tolist()}"
+    assert np.array_equal(bits(t), bits(ot)), f"{what}: hit times differ"
+    nb = int((bits(data) != bits(rgba)).any(-1).sum())
+    assert nb == 0, f"{what}: {nb} pixels differ in RGBA"
+    assert ctx.total_rays == st.rays, f"{what}: ray count {ctx.total_rays} != oracle {st.rays}"
+
+
+@pytest.fixture(scope="module")
+def scenes(R, O):
+    out = {}
+    for det in (False, True):
+        s = R.main_scene(deterministic=det)
+        out[det] = (s, O.Scene(s.tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE), O.Scene(s.tris.view(O.TRI_DTYPE), O.ACCEL_BVH))
+    return out
+
+
+def test_golden_64(R, scenes, golden):
+    """main.rs's own 64x64 frame against the committed golden vectors (oracle, reference octree)."""
+    stats, g = golden
+    for det, tag in ((False, "shipped"), (True, "det")):
+        data, prim, t, ctx, _ = gpu_render(R, scenes[det][0], R.main_viewport(64, 64, 5, 1))
+        assert np.array_equal(prim, g[f"{tag}_prim"])
+        assert np.array_equal(bits(t), bits(g[f"{tag}_t"]))
+        assert np.array_equal(bits(data), bits(g[f"{tag}_rgba"]))
+        assert ctx.total_rays == stats[f"{tag}_rays_64"]
+
+
+@pytest.mark.parametrize("det", [True, False])
+def test_vs_reference_octree_640x480(R, O, scenes, det):
+    """Config 0/2 at the reference's 640x480 size: octree (reference algorithm) oracle, all bounces."""
+    s, oct_sc, _ = scenes[det]
+    assert_bit_exact(gpu_render(R, s, R.main_viewport(640, 480, 5, 1), seed=7),
+                     oct_sc.render(O.main_viewport(640, 480, 5, 1), seed=7), f"640x480 det={det}")
+
+
+def test_deterministic_rgb_within_1_255(R, O, scenes):
+    """The north_star's stated RGB criterion, evaluated in write_png's u8 domain."""
+    s, oct_sc, _ = scenes[True]
+    data = gpu_render(R, s, R.main_viewport(640, 480, 5, 1))[0]
+    rgba = oct_sc.render(O.main_viewport(640, 480, 5, 1))[0]
+    q, oq = O.quantize_rgb8(data).astype(np.int32), O.quantize_rgb8(rgba).astype(np.int32)
+    ok = (np.abs(q - oq).max(-1) <= 1).mean()
+    assert ok >= 0.999
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (7, 5), (16, 8), (17, 9), (333, 217), (1000, 3)])
+def test_ragged_sizes(R, O, scenes, wh):
+    s, _, bvh = scenes[False]
+    assert_bit_exact(gpu_render(R, s, R.main_viewport(*wh, 5, 1), seed=2), bvh.render(O.main_viewport(*wh, 5, 1), seed=2),
+                     f"{wh}")
+
+
+@pytest.mark.parametrize("maxdepth", [1, 2, 3, 8, 16])
+def test_maxdepth(R, O, scenes, maxdepth):
+    s, _, bvh = scenes[False]
+    assert_bit_exact(gpu_render(R, s, R.main_viewport(320, 200, maxdepth, 1), seed=5),
+                     bvh.render(O.main_viewport(320, 200, maxdepth, 1), seed=5), f"maxdepth {maxdepth}")
+
+
+def test_maxdepth_above_cap_is_an_error(R, scenes):
+    from rust_raytrace_b200._lib import RtbError
+    v = R.main_viewport(8, 8, 17, 1)
+    with pytest.raises(RtbError):
+        gpu_render(R, scenes[True][0], v)
+
+
+def test_multisample_jitter_bit_exact(R, O, scenes):
+    """spp > 1: jittered primary rays (raytrace.rs:1382-1386) and in-order accumulation (:1422-1426)."""
+    s, _, bvh = scenes[False]
+    assert_bit_exact(gpu_render(R, s, R.main_viewport(240, 160, 5, 5), seed=9),
+                     bvh.render(O.main_viewport(240, 160, 5, 5), seed=9), "spp=5")
+
+
+def test_teapot_2k_prim_ids(R, O, scenes):
+    """BASELINE config 2: teapot_tri.obj at 2560x1440, 1 spp, deterministic materials — bit-exact ids on
+    all 3,686,400 pixels (oracle in BVH mode, which tests/test_oracle.py pins to the octree)."""
+    s, _, bvh = scenes[True]
+    assert_bit_exact(gpu_render(R, s, R.main_viewport(2560, 1440, 5, 1)), bvh.render(O.main_viewport(2560, 1440, 5, 1)),
+                     "2K deterministic")
+
+
+def test_teapot_4k_multibounce(R, O, scenes):
+    """BASELINE config 3: 3840x2160, maxdepth 5, shipped materials (Matte teapot, fuzzy mirrors)."""
+    s, oct_sc, bvh = scenes[False]
+    gpu = gpu_render(R, s, R.main_viewport(3840, 2160, 5, 1), seed=7)
+    assert_bit_exact(gpu, bvh.render(O.main_viewport(3840, 2160, 5, 1), seed=7), "4K shipped")
+    assert gpu[3].total_rays == 14259831          # rays of the reference octree algorithm, seed 7
+    # a band of the same frame against the reference's own octree traversal
+    rows = (1000, 1064)
+    rgba, prim, t, _ = oct_sc.render(O.main_viewport(3840, 2160, 5, 1), seed=7, rows=rows)
+    sl = slice(*rows)
+    assert np.array_equal(gpu[1][sl], prim[sl]) and np.array_equal(bits(gpu[2][sl]), bits(t[sl]))
+    assert np.array_equal(bits(gpu[0][sl]), bits(rgba[sl]))
+
+
+def test_bvh_equals_gpu_bruteforce(R, scenes):
+    """Size-independent property: the LBVH traversal returns exactly what a linear scan over every
+    primitive returns (same kernel, RTB_FLAG_BRUTE) — ids, t and colour, all bounces."""
+    from rust_raytrace_b200 import _lib
+    s = scenes[False][0]
+    v = R.main_viewport(1280, 720, 5, 1)
+    a = gpu_render(R, s, v, seed=3)
+    vb = _lib.RtbView.from_buffer_copy(v)
+    vb.flags |= _lib.RTB_FLAG_BRUTE
+    b = gpu_render(R, s, vb, seed=3)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+    assert a[3].total_rays == b[3].total_rays
+
+
+def test_rotated_camera(R, O, scenes):
+    s, _, bvh = scenes[True]
+    args = ((400, 300), (1.0, 0.75), [1.0, -1.0, 0.5], None, 60.0, 0.4, 5, 1)
+    rv = R.create_viewport(*args[:3], R.unit([0.2, 0.15, 1.0]), *args[4:])
+    ov = O.create_viewport(*args[:3], O.unit([0.2, 0.15, 1.0]), *args[4:])
+    assert_bit_exact(gpu_render(R, s, rv), bvh.render(ov), "rotated camera")
+
+
+def test_empty_and_tiny_scenes(R, O):
+    v, ov = R.main_viewport(64, 48, 5, 1), O.main_viewport(64, 48, 5, 1)
+    only_dummy = R.Scene(R.make_dummy_triangle())
+    data, prim, t, ctx, _ = gpu_render(R, only_dummy, v)
+    assert not prim.any() and ctx.total_rays == 64 * 48
+    sky = np.array([128 / 255, 180 / 255, 1.0, 0.0], np.float32)           # raytrace.rs:1264
+    assert np.array_equal(bits(data), np.broadcast_to(bits(sky), data.shape))
+    # 1, 2, 5 triangles (root leaf / one split / two levels)
+    surf = R.SurfaceKind.Reflective(0.0, R.make_color((200, 50, 50)), 0.5)
+    tris = [R.make_dummy_triangle()]
+    for k in range(5):
+        z = 3.0 + k
+        tris.append(R.make_triangle([[1 + k * 0.1, -1, z], [3, 0.2 * k, z], [1.5, 1, z + 0.5]], surf, 0.05))
+        arr = np.concatenate(tris)
+        sc = R.Scene(arr)
+        osc = O.Scene(arr.view(O.TRI_DTYPE), O.ACCEL_TRIVIAL)
+        assert_bit_exact(gpu_render(R, sc, v), osc.render(ov), f"{k + 1} triangles")
+
+
+def test_root_cube_cull(R, O):
+    """Triangles outside the reference's octree root are invisible there (raytrace.rs:795-805)."""
+    surf = R.SurfaceKind.Solid(R.make_color((10, 200, 10)))
+    arr = np.concatenate([R.make_dummy_triangle(),
+                          R.make_triangle([[1, -1, 50], [3, 0, 50], [1.5, 1, 50]], surf, 0.0),    # z=50: outside
+                          R.make_triangle([[1, -1, 6], [3, 0, 6], [1.5, 1, 6]], surf, 0.0)])
+    v, ov = R.main_viewport(96, 96, 2, 1), O.main_viewport(96, 96, 2, 1)
+    got = gpu_render(R, R.Scene(arr), v)
+    assert got[4].stats.rays == 96 * 96 and set(np.unique(got[1])) == {0, 2}
+    assert_bit_exact(got, O.Scene(arr.view(O.TRI_DTYPE), O.ACCEL_OCTREE).render(ov), "cull")
+    assert R.Scene(arr).info().n_prims == 1 and R.Scene(arr, boxes=None).info().n_prims == 2
+
+
+def test_sphere_scene_config1(R, O):
+    """BASELINE config 1 ('circles'): tessellated spheres (make_sphere, raytrace.rs:464-529) over a disk,
+    primary + one bounce.  The analytic-sphere scene of circles_2k.png no longer exists in the reference."""
+    rng = np.random.RandomState(1)
+    parts = [R.make_dummy_triangle()]
+    for k in range(6):
+        c = [float(rng.uniform(-1, 3)), float(rng.uniform(-3, 3)), float(rng.uniform(5, 9))]
+        col = R.make_color(tuple(int(x) for x in rng.randint(30, 255, 3)))
+        surf = R.SurfaceKind.Reflective(0.0, col, 0.6) if k == 0 else R.SurfaceKind.Solid(col)
+        parts.append(R.make_sphere(c, 0.8, (8, 16), surf, 0.0))
+    parts.append(R.make_disk([-2.0, 0.0, 8.0], R.unit([1.0, 0.0, 0.05]), 8.0, 0.1, 40,
+                             R.SurfaceKind.Matte(R.make_color((90, 90, 90)), 0.3), R.SurfaceKind.Solid([0.1, 0.1, 0.1]), -1.0))
+    arr = np.concatenate(parts)
+    v, ov = R.main_viewport(512, 288, 2, 1), O.main_viewport(512, 288, 2, 1)
+    assert_bit_exact(gpu_render(R, R.Scene(arr), v, seed=4), O.Scene(arr.view(O.TRI_DTYPE), O.ACCEL_BVH).render(ov, seed=4),
+                     "spheres")
+
+
+def test_stats_variant_and_bvh_shape(R, scenes):
+    s = scenes[False][0]
+    inf = s.info()
+    assert inf.n_tris == 6721 and inf.n_prims == 6720 and inf.max_leaf <= 4 and inf.tree_height < 62
+    nodes, order = s.download_bvh()
+    assert sorted(order.tolist()) == list(range(1, 6721))
+    a = gpu_render(R, s, R.main_viewport(640, 360, 5, 1), seed=1)
+    b = gpu_render(R, s, R.main_viewport(640, 360, 5, 1), seed=1, stats=True)
+    assert np.array_equal(bits(a[0]), bits(b[0]))
+    st = b[4].stats
+    assert st.node_tests > st.rays and st.tri_tests > 0 and st.node_tests / st.rays < 200
+
+
+def test_quantiser_on_gpu(R, O):
+    px = np.random.RandomState(0).uniform(-0.2, 1.2, (1000, 4)).astype(np.float32)
+    px[0, :3] = [np.nan, 1.0, 0.0]
+    assert np.array_equal(R.quantize_rgb8(px), O.quantize_rgb8(px))
+
+
+def test_multi_gpu_tiles_identical(R, scenes):
+    """Image bands split over all visible GPUs must reproduce the single-GPU frame bit for bit."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    s = R.main_scene(False)
+    v = R.main_viewport(1920, 1083, 5, 1)
+    one = gpu_render(R, s, v, seed=6, threads=1)
+    s2 = R.main_scene(False)
+    many = gpu_render(R, s2, v, seed=6, threads=n)
+    assert np.array_equal(one[1], many[1]) and np.array_equal(bits(one[0]), bits(many[0]))
+    assert one[3].total_rays == many[3].total_rays
+
+
+def test_progressive_psnr(R, O, scenes):
+    """Stochastic mode: samples partitioned + peer reduce; PSNR >= 40 dB against a high-spp oracle render."""
+    s, _, bvh = scenes[False]
+    W, H = 160, 120
+    ref = bvh.render(O.main_viewport(W, H, 5, 1024), seed=99)[0][..., :3]
+    v = R.main_viewport(W, H, 5, 256)
+    data = R.new_image(v)
+    R.B200RayCaster(seed=1).walk_rays_progressive(v, R.main_scene(False), data, threads=0)
+    mse = float(np.mean((np.clip(data[..., :3], 0, 1) - np.clip(ref, 0, 1)) ** 2))
+    psnr = 10 * np.log10(1.0 / mse)
+    assert psnr >= 40.0, psnr

@@ -1,0 +1,128 @@
+"""CPU tests of the product's host-side scene preparation (C++ in librtb.so) against the oracle's
+independent restatement, byte for byte; the C ABI surface; the band partition."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol(R):
+    from rust_raytrace_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set()
+    for hdr in ("rtb.h", "rtb_host.h"):
+        text = open(os.path.join(root, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(rtbh?_[a-z0-9_]+)\s*\(", text))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.RTB_SYMBOLS + _lib.RTBH_SYMBOLS)
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert getattr(L, name) is not None
+
+
+def test_struct_sizes_match_the_header(R):
+    from rust_raytrace_b200 import _lib
+    assert _lib.TRI_DTYPE.itemsize == 140
+    assert C.sizeof(_lib.RtbView) == 88
+    assert C.sizeof(_lib.RtbStats) == 48
+
+
+def test_main_scene_bytes_equal_oracle(R, O, teapot_mesh):
+    verts, faces = teapot_mesh
+    for det in (False, True):
+        assert R.main_scene(det).tris.tobytes() == O.main_scene_tris(verts, faces, det).tobytes()
+
+
+@pytest.mark.parametrize("wh", [(64, 64), (640, 480), (2560, 1440), (3840, 2160), (7680, 4320), (333, 217), (1, 1)])
+def test_viewport_bytes_equal_oracle(R, O, wh):
+    a, b = R.main_viewport(*wh, maxdepth=5, spp=1), O.main_viewport(*wh, maxdepth=5, spp=1)
+    assert bytes(a)[:64] == bytes(b)[:64]
+
+
+def test_rotated_camera_and_transform(R, O):
+    d = [0.3, -0.2, 0.9]
+    assert R.create_transform(R.unit(d), 0.7).tobytes() == O.create_transform(O.unit(d), 0.7).tobytes()
+    a = R.create_viewport((100, 50), (1.0, 0.5), [1, 2, 3], R.unit(d), 70.0, 0.3, 4, 2)
+    b = O.create_viewport((100, 50), (1.0, 0.5), [1, 2, 3], O.unit(d), 70.0, 0.3, 4, 2)
+    assert bytes(a)[:64] == bytes(b)[:64]
+
+
+def test_sphere_and_disk_generators(R, O):
+    s = R.make_sphere([1, 2, 3], 1.5, (8, 12), R.SurfaceKind.Matte(R.make_color((10, 20, 30)), 0.3), 0.02)
+    so = O.make_sphere([1, 2, 3], 1.5, 8, 12, O.Surface(O.OR_MATTE, O.make_color(10, 20, 30), 0.3), 0.02)
+    assert len(s) == 8 * 12 * 2 - 2 * 12 and s.tobytes() == so.tobytes()
+    with pytest.raises(ValueError):
+        R.make_sphere([0, 0, 0], 1.0, (7, 8), R.SurfaceKind.Solid([1, 1, 1]), 0.0)   # odd lat: reference asserts
+    d = R.make_disk([0, 1, 2], R.unit([0.2, 0.1, -1]), 2.0, 0.1, 17, R.SurfaceKind.Reflective(0.01, [1, 1, 1], 0.5),
+                    R.SurfaceKind.Solid([0, 0, 0]), -1.0)
+    do = O.make_disk([0, 1, 2], O.unit([0.2, 0.1, -1]), 2.0, 0.1, 17, O.Surface(O.OR_REFLECTIVE, [1, 1, 1], 0.5, 0.01),
+                     O.Surface(O.OR_SOLID, [0, 0, 0]), -1.0)
+    assert len(d) == 68 and d.tobytes() == do.tobytes()
+
+
+def test_obj_text_roundtrip(R, O, teapot_mesh, tmp_path):
+    verts, faces = teapot_mesh
+    p = tmp_path / "pot.obj"
+    with open(p, "w") as fh:
+        fh.write("# comment\nvn 0 0 1\n")
+        for v in verts[:400]:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for f in faces:
+            if f.max() <= 400:
+                fh.write("f %d//1 %d//2 %d//3\n" % tuple(f))   # the a//n form of teapot_tri.obj
+    sel = faces[(faces.max(axis=1) <= 400)]
+    surf = R.SurfaceKind.Solid([1, 0, 0])
+    tf = R.create_transform(R.unit([0, 0.3, 1]), R.to_radians(270.0))
+    a = R.obj_parser.parse_obj(str(p), [0, 0.5, 5], 1.0, tf, surf, 0.05)
+    b = R.obj_parser.mesh_to_triangles(verts[:400], sel, [0, 0.5, 5], 1.0, tf, surf, 0.05)
+    assert len(a) == len(sel) > 100 and a.tobytes() == b.tobytes()
+    ov, of = O.parse_obj_file(str(p))
+    assert np.array_equal(ov, verts[:400]) and np.array_equal(of, sel)
+    with pytest.raises(ValueError):
+        R.obj_parser.parse_obj(str(tmp_path / "missing.obj"), [0, 0, 0], 1.0, tf, surf, 0.0)
+
+
+def test_degenerate_triangle_is_an_error_not_a_crash(R):
+    with pytest.raises(ValueError):
+        R.make_triangle([[0, 0, 0], [1, 1, 1], [2, 2, 2]], R.SurfaceKind.Solid([0, 0, 0]), 0.0)
+
+
+def test_root_cube_membership(R):
+    from rust_raytrace_b200 import _lib
+    L = _lib.lib()
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    inside = R.make_triangle([[0, 0, 5], [1, 0, 5], [0, 1, 5]], R.SurfaceKind.Solid([1, 1, 1]), 0.0)
+    outside = R.make_triangle([[0, 0, 50], [1, 0, 50], [0, 1, 50]], R.SurfaceKind.Solid([1, 1, 1]), 0.0)
+    assert L.rtbh_box_contains_polygon(f3([0, 0, 20.1]), 20.0, inside.ctypes.data) == 1
+    assert L.rtbh_box_contains_polygon(f3([0, 0, 20.1]), 20.0, outside.ctypes.data) == 0
+
+
+def test_band_partition_covers_every_row_once(R):
+    from rust_raytrace_b200 import _lib
+    L = _lib.lib()
+    for H in (1, 7, 8, 9, 64, 1440, 2160, 2161):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(H, np.int32)
+            for rank in range(world):
+                rows = np.zeros(H, np.uint32)
+                n = L.rtb_partition_rows(H, rank, world, rows.ctypes.data, H)
+                assert n >= 0
+                seen[rows[:n]] += 1
+                assert np.all((rows[:n] // 8) % world == rank)
+            assert np.all(seen == 1)
+    assert L.rtb_partition_rows(10, 3, 2, None, 0) < 0
+
+
+def test_gpu_path_fails_loudly_without_a_device(R):
+    """No CPU fallback: on a machine without CUDA the render call must raise, not produce pixels."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rust_raytrace_b200._lib import RtbError
+    v = R.main_viewport(8, 8)
+    with pytest.raises(RtbError) as e:
+        R.B200RayCaster().walk_rays(v, R.main_scene(), R.new_image(v), threads=1)
+    assert e.value.code == -1

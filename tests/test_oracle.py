@@ -1,0 +1,113 @@
+"""CPU tests that pin the oracle: the reference's own known-answer test, the structural numbers of
+the reference scene/octree, octree == brute force == oracle-BVH, and the committed golden vectors."""
+import numpy as np
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_face_collision_kat(O):
+    # raytrace_lib/src/raytrace.rs:735-750 — the reference's only hot-path-adjacent unit test
+    assert O.lib().or_selftest_face_collision() == 1
+
+
+def test_scene_and_octree_structure(O, teapot_mesh, golden):
+    stats, _ = golden
+    verts, faces = teapot_mesh
+    assert verts.shape == (3644, 3) and faces.shape == (6320, 3)
+    tris = O.main_scene_tris(verts, faces)
+    assert len(tris) == 6721 == stats["n_tris"]          # 1 dummy + 6320 teapot + 2 x 200 disk
+    st = O.Scene(tris, O.ACCEL_OCTREE).tree_stats()
+    # build_bounding_box(tris, (0,0,20.1), 20, 10, 19)  main.rs:160-164
+    assert (st.nodes, st.leaves, st.leaf_refs, st.max_leaf, st.max_depth, st.leaves_at_maxdepth) == \
+        (204894, 169754, 2935330, 59, 10, 131930)
+
+
+def test_golden_64(O, teapot_mesh, golden):
+    stats, g = golden
+    verts, faces = teapot_mesh
+    for det, tag in ((False, "shipped"), (True, "det")):
+        sc = O.Scene(O.main_scene_tris(verts, faces, deterministic=det), O.ACCEL_OCTREE)
+        rgba, prim, t, st = sc.render(O.main_viewport(64, 64, 5, 1), seed=0, threads=2)
+        assert np.array_equal(prim, g[f"{tag}_prim"])
+        assert np.array_equal(bits(t), bits(g[f"{tag}_t"]))
+        assert np.array_equal(bits(rgba), bits(g[f"{tag}_rgba"]))
+        assert st.rays == stats[f"{tag}_rays_64"]
+
+
+def test_octree_equals_bruteforce_and_bvh(O, teapot_mesh):
+    verts, faces = teapot_mesh
+    tris = O.main_scene_tris(verts, faces, deterministic=False)
+    v = O.main_viewport(200, 150, maxdepth=5, spp=1)
+    ref = O.Scene(tris, O.ACCEL_OCTREE).render(v, seed=3)
+    for accel in (O.ACCEL_TRIVIAL, O.ACCEL_BVH):
+        got = O.Scene(tris, accel).render(v, seed=3)
+        assert np.array_equal(ref[1], got[1])
+        assert np.array_equal(bits(ref[2]), bits(got[2]))
+        assert np.array_equal(bits(ref[0]), bits(got[0]))
+        assert ref[3].rays == got[3].rays
+    assert ref[3].nan_t_hits == 0
+    # work per primary ray of the reference algorithm: ~199 box tests, ~189 triangle tests
+    v1 = O.main_viewport(160, 120, maxdepth=1, spp=1)
+    st = O.Scene(tris, O.ACCEL_OCTREE).render(v1)[3]
+    n = 160 * 120
+    assert 150 < st.box_tests / n < 250 and 150 < st.tri_tests / n < 230 and st.rays == n
+
+
+def test_thread_count_does_not_change_the_image(O, teapot_mesh):
+    verts, faces = teapot_mesh
+    sc = O.Scene(O.main_scene_tris(verts, faces), O.ACCEL_BVH)
+    v = O.main_viewport(96, 64, maxdepth=5, spp=3)
+    a = sc.render(v, seed=11, threads=1)
+    b = sc.render(v, seed=11, threads=4)
+    assert np.array_equal(bits(a[0]), bits(b[0])) and a[3].rays == b[3].rays
+
+
+def test_triangle_intersects_edge_cases(O):
+    import ctypes as C
+    surf = O.Surface(O.OR_SOLID, [1, 0, 0])
+    tri = O.make_triangle([[0, 0, 1], [1, 0, 1], [0, 1, 1]], surf, 0.1)
+    t, p = C.c_float(), (C.c_float * 3)()
+    f3 = lambda v: (C.c_float * 3)(*v)  # noqa: E731
+    L = O.lib()
+    # straight hit in the interior: Back or Front by the sign of dir.norm
+    face = L.or_triangle_intersects(tri.ctypes.data, f3([0.3, 0.3, 0]), f3([0, 0, 1]), C.byref(t), p)
+    assert face in (1, 2) and abs(t.value - 1.0) < 1e-6
+    # behind the origin: t < 0 -> miss (raytrace.rs:403)
+    assert L.or_triangle_intersects(tri.ctypes.data, f3([0.3, 0.3, 2]), f3([0, 0, 1]), C.byref(t), p) == 0
+    # near an edge: edge_thickness 0.1 -> Edge* face (raytrace.rs:419)
+    face = L.or_triangle_intersects(tri.ctypes.data, f3([0.3, 0.001, 0]), f3([0, 0, 1]), C.byref(t), p)
+    assert face in (3, 4)
+    # outside: miss
+    assert L.or_triangle_intersects(tri.ctypes.data, f3([0.9, 0.9, 0]), f3([0, 0, 1]), C.byref(t), p) == 0
+
+
+def test_degenerate_triangle_is_rejected(O):
+    import pytest
+    with pytest.raises(ValueError):
+        O.make_triangle([[0, 0, 0], [1, 1, 1], [2, 2, 2]], O.Surface(O.OR_SOLID, [0, 0, 0]), 0.0)
+
+
+def test_quantiser_matches_rust_as_u8(O):
+    # (c*255.) as u8: truncation, saturation, NaN -> 0  (raytrace.rs:1468-1473)
+    px = np.array([[0.0, 0.5, 1.0, 0], [-1.0, 2.0, np.nan, 0], [0.999, 128 / 255, 180 / 255, 0]], np.float32)
+    q = O.quantize_rgb8(px)
+    assert q.tolist() == [[0, 127, 255], [0, 255, 0], [254, 128, 180]]
+
+
+def test_rng_is_a_24bit_uniform(O):
+    xs = np.array([O.lib().or_rng_f32(5, 17, 2, i) for i in range(2000)], np.float32)
+    assert xs.min() >= 0.0 and xs.max() < 1.0
+    assert np.all(xs * 16777216.0 == np.floor(xs * 16777216.0))
+    assert abs(xs.mean() - 0.5) < 0.03
+    assert O.lib().or_rng_f32(5, 17, 2, 0) != O.lib().or_rng_f32(5, 18, 2, 0)
+
+
+def test_pixel_ray_geometry(O):
+    v = O.main_viewport(640, 480)
+    r = O.pixel_ray(v, 240, 320)
+    o, d = r[0:3], r[3:6]
+    # camera at (2,0,0) looking down +z (main.rs:166-173); ray origin is the viewport point, not the eye
+    assert abs(np.linalg.norm(d) - 1.0) < 1e-6 and d[2] > 0.99
+    assert abs(o[2]) < 1e-6 and abs(o[0] - 2.0) < 0.01 and abs(o[1]) < 0.01
