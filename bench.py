@@ -188,7 +188,11 @@ def run_gpu(args):
 
     d_rgba = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # an explicit (non-null) stream: handle 0 would mean "the library's own stream" to rtb_render_device,
+    # and torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
 
     def step(stats=None):
         _lib.check(L.rtb_render_device(h, C.byref(view), 0, rank, world, d_rgba.data_ptr(), None, None,

@@ -109,8 +109,13 @@ template <bool STATS>
 __device__ __forceinline__ Hit closest_hit(const SceneDev& sc, V3 o, V3 d, bool brute, unsigned long long& n_node,
                                            unsigned long long& n_tri) {
     Hit h; h.t = FLT_MAX; h.slot = -1; h.orig = 0xffffffffu;
+    if (sc.n_prims == 0u) return h;   // empty scene (only the dummy triangle): everything is sky
     // slab-test constants (not part of the exactness contract; boxes are padded, see rtb_lbvh.cu)
-    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    // |1/d| is clamped to 1e30 so that a zero direction component gives +-huge instead of inf: with inf the
+    // fused form lo*inv - o*inv turns into inf - inf = NaN on one plane only and the slab collapses.
+    const float ix = fminf(fmaxf(1.0f / d.x, -1e30f), 1e30f);
+    const float iy = fminf(fmaxf(1.0f / d.y, -1e30f), 1e30f);
+    const float iz = fminf(fmaxf(1.0f / d.z, -1e30f), 1e30f);
     const float ox = -o.x * ix, oy = -o.y * iy, oz = -o.z * iz;
     float tbest = FLT_MAX;   // +inf-like culling bound until the first hit
 
