@@ -87,8 +87,10 @@ typedef struct RtbView {
 enum {
     RTB_FLAG_SUM_ONLY = 1u,   /* write the un-normalised sample sum (for a later cross-GPU reduce) */
     RTB_FLAG_STATS    = 2u,   /* also count node/triangle tests (slower kernel variant)            */
-    RTB_FLAG_BRUTE    = 4u    /* validation: ignore the BVH, test every primitive (the GPU analogue of
+    RTB_FLAG_BRUTE    = 4u,   /* validation: ignore the BVH, test every primitive (the GPU analogue of
                                  build_trivial_bounding_box, raytrace.rs:847-856)                  */
+    RTB_FLAG_MEGAKERNEL = 8u  /* A/B: the one-kernel-per-frame renderer (rtb_trace.cu) instead of the
+                                 default wavefront pipeline (rtb_wavefront.cu); same results        */
 };
 
 typedef struct RtbStats {

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "librtb.so")
 
 RTB_OK, RTB_ERR_NO_DEVICE, RTB_ERR_CUDA, RTB_ERR_INVALID, RTB_ERR_NOMEM = 0, -1, -2, -3, -4
 RTB_SOLID, RTB_MATTE, RTB_REFLECTIVE = 0, 1, 2
-RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE = 1, 2, 4
+RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL = 1, 2, 4, 8
 RTB_MAX_DEPTH = 16
 
 # numpy mirror of RtbTriangle (35 x 4 bytes; reference field order raytrace.rs:326-337)

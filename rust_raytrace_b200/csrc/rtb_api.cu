@@ -1,8 +1,11 @@
 // rtb_api.cu — the C ABI of include/rtb.h: device selection, scene upload + LBVH build,
 // frame rendering into host or device buffers, progressive multi-GPU rendering.
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "rtb_internal.cuh"
 #include "host/raytrace_host.hpp"
@@ -47,8 +50,16 @@ void free_gpu_scene(GpuScene& g) {
     if (g.stream) cudaStreamSynchronize(g.stream);
     cudaFree(g.d_nodes); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
     cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t);
+    for (auto& l : g.lanes) {
+        cudaFree(l.d_ws);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.st) cudaStreamDestroy(l.st);
+    }
+    if (g.fork_ev) cudaEventDestroy(g.fork_ev);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
+    for (auto& e : g.chunk_ev) if (e) cudaEventDestroy(e);
+    if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
     if (g.stream) cudaStreamDestroy(g.stream);
     g = GpuScene();
 }
@@ -68,6 +79,7 @@ int ensure_framebuffer(GpuScene& g, size_t pixels, bool want_prim, bool want_t) 
 int check_view(const RtbView* v) {
     if (!v) return fail(RTB_ERR_INVALID, "view is NULL");
     if (v->width == 0 || v->height == 0) return fail(RTB_ERR_INVALID, "viewport has zero width or height");
+    if (v->maxdepth == 0) return fail(RTB_ERR_INVALID, "maxdepth must be >= 1");
     if (v->maxdepth > RTB_MAX_DEPTH)
         return fail(RTB_ERR_INVALID, "maxdepth " + std::to_string(v->maxdepth) + " exceeds RTB_MAX_DEPTH");
     if (v->spp == 0) return fail(RTB_ERR_INVALID, "samples_per_pixel must be >= 1");
@@ -96,7 +108,83 @@ ViewDev make_view(const RtbView& v, uint32_t rank, uint32_t world, bool compact)
 SceneDev scene_dev(const GpuScene& g, uint32_t n_prims) {
     SceneDev s;
     s.nodes = g.d_nodes; s.tri = g.d_tri; s.shade = g.d_shade; s.n_prims = n_prims; s.n_nodes = g.n_nodes;
+    s.height = g.height;
     return s;
+}
+
+// Pixels of the image this rank renders (rows of its 8-row bands that lie inside the image).
+uint64_t owned_pixels(const ViewDev& vd) {
+    uint64_t rows = 0;
+    for (uint32_t b = vd.band_begin; b < vd.band_begin + vd.my_tile_rows; ++b) {
+        const uint32_t row0 = (b * vd.tile_world + vd.tile_rank) * RTB_TILE_H;
+        if (row0 < vd.height) rows += std::min<uint32_t>(RTB_TILE_H, vd.height - row0);
+    }
+    return rows * vd.width;
+}
+
+// One frame (all samples, all bounces) of this rank's bands on stream `st`.  Default: the wavefront
+// pipeline; RTB_FLAG_MEGAKERNEL selects the one-kernel renderer.  *primary_rays is what must be added to
+// counters->rays afterwards (the wavefront counts bounce rays on the device, primaries on the host).
+int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd, float4* d_rgba, uint32_t* d_prim,
+                 float* d_t, cudaStream_t st, uint32_t* launches, uint64_t* primary_rays) {
+    if (vd.flags & RTB_FLAG_MEGAKERNEL)
+        return rtb_launch_trace(scene_dev(g, n_prims), vd, d_rgba, d_prim, d_t, g.d_counters, st, launches);
+    const uint32_t n_slots = vd.my_tile_rows * 2u * ((vd.width + 7u) / 8u) * 32u;
+    const size_t need = rtb_wf_workspace_bytes(n_slots, vd.maxdepth ? vd.maxdepth : 1, (vd.s_end - vd.s_begin) > 1);
+    if (lane.ws_bytes < need) {
+        RTB_CUDA(cudaDeviceSynchronize());
+        if (lane.d_ws) RTB_CUDA(cudaFree(lane.d_ws));
+        lane.d_ws = nullptr; lane.ws_bytes = 0;
+        RTB_CUDA(cudaMalloc(&lane.d_ws, need + need / 16));     // slack: pieces differ by a band
+        lane.ws_bytes = need + need / 16;
+    }
+    *primary_rays += owned_pixels(vd) * (uint64_t)(vd.s_end - vd.s_begin);
+    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, lane.d_ws, d_rgba, d_prim, d_t, g.d_counters, st, launches);
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? std::max(1, atoi(e)) : dflt;
+}
+
+// Renders the bands described by `whole` in `pieces` pieces, round-robin over `n_lanes` compute streams that are
+// forked from and joined back into `st`.  Why: every stage of the wavefront pipeline ends with a drain in which a
+// few long rays keep a few warps alive (each bounce level costs >= ~0.15 ms however few rays it has); with
+// several independent pieces in flight on different streams the hardware fills one piece's drain with another
+// piece's blocks.  after_piece(c, piece_view, lane_stream) runs after a piece's kernels are queued.
+template <class F>
+int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d_rgba, uint32_t* d_prim, float* d_t,
+                  cudaStream_t st, uint32_t pieces, uint32_t n_lanes, uint32_t* launches, uint64_t* primary, F after_piece) {
+    pieces = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(pieces, RTB_MAX_CHUNKS), whole.my_tile_rows));
+    n_lanes = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(n_lanes, RTB_MAX_LANES), pieces));
+    if (whole.flags & RTB_FLAG_MEGAKERNEL) n_lanes = 1;
+    for (uint32_t l = 0; l < n_lanes; ++l) {
+        GpuLane& lane = g.lanes[l];
+        if (!lane.done) RTB_CUDA(cudaEventCreateWithFlags(&lane.done, cudaEventDisableTiming));
+        if (l > 0 && !lane.st) RTB_CUDA(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
+    }
+    if (n_lanes > 1) {
+        if (!g.fork_ev) RTB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(g.fork_ev, st));
+        for (uint32_t l = 1; l < n_lanes; ++l) RTB_CUDA(cudaStreamWaitEvent(g.lanes[l].st, g.fork_ev, 0));
+    }
+    for (uint32_t c = 0; c < pieces; ++c) {
+        ViewDev vd = whole;
+        vd.band_begin = whole.band_begin + (uint32_t)((uint64_t)whole.my_tile_rows * c / pieces);
+        vd.my_tile_rows = whole.band_begin + (uint32_t)((uint64_t)whole.my_tile_rows * (c + 1) / pieces) - vd.band_begin;
+        if (vd.my_tile_rows == 0) continue;
+        const uint32_t l = c % n_lanes;
+        cudaStream_t ls = l == 0 ? st : g.lanes[l].st;     // lane 0 is the caller's stream itself
+        int rc = launch_frame(g, g.lanes[l], n_prims, vd, d_rgba, d_prim, d_t, ls, launches, primary);
+        if (rc != RTB_OK) return rc;
+        rc = after_piece(c, vd, ls);
+        if (rc != RTB_OK) return rc;
+    }
+    for (uint32_t l = 1; l < n_lanes; ++l) {
+        RTB_CUDA(cudaEventRecord(g.lanes[l].done, g.lanes[l].st));
+        RTB_CUDA(cudaStreamWaitEvent(st, g.lanes[l].done, 0));
+    }
+    return RTB_OK;
 }
 
 }  // namespace
@@ -207,6 +295,7 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
         cudaFree(d_keep);
         g.d_nodes = br.d_nodes; g.d_tri = br.d_tri; g.d_shade = br.d_shade; g.d_prim_order = br.d_prim_order;
         g.n_nodes = br.n_nodes;
+        g.height = br.tree_height;
         if (rc != RTB_OK) return bail(rc);
         if (gi == 0) {
             s->info.n_nodes = br.n_nodes; s->info.n_leaves = br.n_leaves; s->info.max_leaf = br.max_leaf;
@@ -261,7 +350,12 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
         RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), st));
         RTB_CUDA(cudaEventRecord(g.ev0, st));
     }
-    rc = rtb_launch_trace(scene_dev(g, s->info.n_prims), vd, (float4*)d_rgba, d_prim, d_t, g.d_counters, st, &launches);
+    uint64_t primary = 0;
+    const size_t px = (size_t)vd.my_tile_rows * RTB_TILE_H * vd.width;
+    const uint32_t pieces = (uint32_t)env_int("RTB_PIECES", (int)std::min<size_t>(RTB_DEFAULT_PIECES_DEVICE, std::max<size_t>(1, px / (1u << 20))));
+    const uint32_t n_lanes = (uint32_t)env_int("RTB_LANES", RTB_DEFAULT_LANES);
+    rc = render_pieces(g, s->info.n_prims, vd, (float4*)d_rgba, d_prim, d_t, st, pieces, n_lanes, &launches, &primary,
+                       [](uint32_t, const ViewDev&, cudaStream_t) { return (int)RTB_OK; });
     if (rc != RTB_OK) return rc;
     if (stats) {
         RTB_CUDA(cudaEventRecord(g.ev1, st));
@@ -271,7 +365,7 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
         float ms = 0.f;
         RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
         std::memset(stats, 0, sizeof *stats);
-        stats->rays = c.rays; stats->node_tests = c.node_tests; stats->tri_tests = c.tri_tests;
+        stats->rays = c.rays + primary; stats->node_tests = c.node_tests; stats->tri_tests = c.tri_tests;
         stats->ms_render = ms; stats->ms_total = now_ms() - t0; stats->kernel_launches = launches; stats->n_gpus = 1;
     }
     return RTB_OK;
@@ -288,54 +382,94 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
     const uint32_t W = view->width, H = view->height;
     const uint32_t tiles_y = (H + RTB_TILE_H - 1) / RTB_TILE_H;
     uint32_t launches = 0;
+    uint64_t primary_total = 0;
 
-    // phase 1: launch every GPU's bands and its strided copy back, all asynchronous
-    for (uint32_t r = 0; r < world; ++r) {
+    // Every GPU renders its 8-row bands (band b -> GPU b % world) into a compact device buffer and copies
+    // them home with one strided cudaMemcpy2DAsync per chunk over its own PCIe link.  The bands of a GPU are
+    // processed in `chunks` pieces so that the D2H copy of piece i overlaps the kernels of piece i+1
+    // (compute stream + copy stream, one event per piece).
+    std::vector<uint32_t> launches_r(world, 0);
+    std::vector<uint64_t> primary_r(world, 0);
+    std::vector<std::string> err_r(world);
+    auto issue = [&](uint32_t r) -> int {
+        int rc = RTB_OK;
+        uint32_t& launches = launches_r[r];
+        uint64_t& primary_total = primary_r[r];
         GpuScene& g = s->gpu[r];
         RTB_CUDA(cudaSetDevice(g.device));
-        const ViewDev vd = make_view(*view, r, world, true);
-        if (vd.my_tile_rows == 0) continue;
-        const size_t pixels = (size_t)vd.my_tile_rows * RTB_TILE_H * W;
+        const ViewDev whole = make_view(*view, r, world, true);
+        if (whole.my_tile_rows == 0) return RTB_OK;
+        const size_t pixels = (size_t)whole.my_tile_rows * RTB_TILE_H * W;
         rc = ensure_framebuffer(g, pixels, prim_out != nullptr, t_out != nullptr);
         if (rc != RTB_OK) return rc;
+        if (!g.copy_stream) {
+            RTB_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+            for (auto& e : g.chunk_ev) RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const uint32_t pieces = (uint32_t)env_int("RTB_PIECES", (int)std::min<size_t>(RTB_DEFAULT_PIECES, std::max<size_t>(1, pixels / (1u << 20))));
+        const uint32_t n_lanes = (uint32_t)env_int("RTB_LANES", RTB_DEFAULT_LANES);
         RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), g.stream));
         RTB_CUDA(cudaEventRecord(g.ev0, g.stream));
-        rc = rtb_launch_trace(scene_dev(g, s->info.n_prims), vd, g.d_rgba, prim_out ? g.d_prim : nullptr,
-                              t_out ? g.d_t : nullptr, g.d_counters, g.stream, &launches);
+        rc = render_pieces(g, s->info.n_prims, whole, g.d_rgba, prim_out ? g.d_prim : nullptr, t_out ? g.d_t : nullptr,
+                           g.stream, pieces, n_lanes, &launches, &primary_total,
+                           [&](uint32_t c, const ViewDev& vd, cudaStream_t ls) -> int {
+            // the piece's bands go home on the copy stream as soon as its kernels are done
+            RTB_CUDA(cudaEventRecord(g.chunk_ev[c], ls));
+            RTB_CUDA(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c], 0));
+            // local band b = image rows [(b*world + r)*8, +8); copy bands [band_begin, band_begin+n)
+            const uint32_t b0 = vd.band_begin, nb = vd.my_tile_rows;
+            const uint32_t last_ty = (b0 + nb - 1) * world + r;
+            const bool ragged = (last_ty == tiles_y - 1) && (H % RTB_TILE_H != 0);
+            const uint32_t full_bands = ragged ? nb - 1 : nb;
+            auto copy_plane = [&](void* host, const void* dev, size_t px_bytes) -> int {
+                const size_t band_bytes = (size_t)RTB_TILE_H * W * px_bytes;
+                char* dst0 = (char*)host + ((size_t)b0 * world + r) * band_bytes;
+                const char* src0 = (const char*)dev + (size_t)b0 * band_bytes;
+                if (full_bands)
+                    RTB_CUDA(cudaMemcpy2DAsync(dst0, band_bytes * world, src0, band_bytes, band_bytes, full_bands,
+                                               cudaMemcpyDeviceToHost, g.copy_stream));
+                if (ragged) {
+                    const size_t rows = H - (size_t)last_ty * RTB_TILE_H;
+                    RTB_CUDA(cudaMemcpyAsync((char*)host + (size_t)last_ty * band_bytes,
+                                             src0 + (size_t)full_bands * band_bytes, rows * W * px_bytes,
+                                             cudaMemcpyDeviceToHost, g.copy_stream));
+                }
+                return RTB_OK;
+            };
+            int rc2;
+            if ((rc2 = copy_plane(rgba_out, g.d_rgba, sizeof(float4))) != RTB_OK) return rc2;
+            if (prim_out && (rc2 = copy_plane(prim_out, g.d_prim, sizeof(uint32_t))) != RTB_OK) return rc2;
+            if (t_out && (rc2 = copy_plane(t_out, g.d_t, sizeof(float))) != RTB_OK) return rc2;
+            return RTB_OK;
+        });
         if (rc != RTB_OK) return rc;
         RTB_CUDA(cudaEventRecord(g.ev1, g.stream));
-        // band b of this rank = image rows [(b*world + r)*8, +8): one strided copy for all full bands,
-        // one more for a ragged last band.
-        const uint32_t last_ty = (vd.my_tile_rows - 1) * world + r;
-        const bool ragged = (last_ty == tiles_y - 1) && (H % RTB_TILE_H != 0);
-        const uint32_t full_bands = ragged ? vd.my_tile_rows - 1 : vd.my_tile_rows;
-        auto copy_plane = [&](void* host, const void* dev, size_t px_bytes) -> int {
-            const size_t band_bytes = (size_t)RTB_TILE_H * W * px_bytes;
-            char* dst0 = (char*)host + (size_t)r * band_bytes;
-            if (full_bands)
-                RTB_CUDA(cudaMemcpy2DAsync(dst0, band_bytes * world, dev, band_bytes, band_bytes, full_bands,
-                                           cudaMemcpyDeviceToHost, g.stream));
-            if (ragged) {
-                const size_t rows = H - (size_t)last_ty * RTB_TILE_H;
-                RTB_CUDA(cudaMemcpyAsync((char*)host + (size_t)last_ty * band_bytes,
-                                         (const char*)dev + (size_t)full_bands * band_bytes, rows * W * px_bytes,
-                                         cudaMemcpyDeviceToHost, g.stream));
-            }
-            return RTB_OK;
-        };
-        if ((rc = copy_plane(rgba_out, g.d_rgba, sizeof(float4))) != RTB_OK) return rc;
-        if (prim_out && (rc = copy_plane(prim_out, g.d_prim, sizeof(uint32_t))) != RTB_OK) return rc;
-        if (t_out && (rc = copy_plane(t_out, g.d_t, sizeof(float))) != RTB_OK) return rc;
+        return RTB_OK;
+    };
+    if (world == 1) {
+        rc = issue(0);
+    } else {
+        // one host thread per GPU: the ~12 launches per piece of one GPU must not queue behind another GPU's
+        std::vector<std::thread> th;
+        std::vector<int> rcs(world, RTB_OK);
+        for (uint32_t r = 0; r < world; ++r)
+            th.emplace_back([&, r]() { rcs[r] = issue(r); if (rcs[r] != RTB_OK) err_r[r] = rtb_last_error(); });
+        for (auto& t : th) t.join();
+        for (uint32_t r = 0; r < world; ++r)
+            if (rcs[r] != RTB_OK) { rc = rcs[r]; g_err = err_r[r]; break; }
     }
-    // phase 2: wait and gather stats
+    if (rc != RTB_OK) return rc;
+    for (uint32_t r = 0; r < world; ++r) { launches += launches_r[r]; primary_total += primary_r[r]; }
+    // wait for every GPU and gather the counters
     RtbStats st;
     std::memset(&st, 0, sizeof st);
     for (uint32_t r = 0; r < world; ++r) {
         GpuScene& g = s->gpu[r];
-        RTB_CUDA(cudaSetDevice(g.device));
-        RTB_CUDA(cudaStreamSynchronize(g.stream));
         const ViewDev vd = make_view(*view, r, world, true);
         if (vd.my_tile_rows == 0) continue;
+        RTB_CUDA(cudaSetDevice(g.device));
+        RTB_CUDA(cudaStreamSynchronize(g.stream));
+        RTB_CUDA(cudaStreamSynchronize(g.copy_stream));
         TraceCounters c;
         RTB_CUDA(cudaMemcpy(&c, g.d_counters, sizeof c, cudaMemcpyDeviceToHost));
         float ms = 0.f;
@@ -343,6 +477,7 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
         st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
         st.ms_render = std::max(st.ms_render, (double)ms);
     }
+    st.rays += primary_total;
     st.ms_total = now_ms() - t0;
     st.kernel_launches = launches;
     st.n_gpus = world;
@@ -362,6 +497,7 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
     const uint32_t s_lo = view->sample_begin, s_hi = (view->sample_begin == 0 && view->sample_end == 0) ? view->spp : view->sample_end;
     const uint32_t n_s = s_hi - s_lo;
     uint32_t launches = 0;
+    uint64_t primary_total = 0;
 
     // phase 1: every GPU accumulates its contiguous share of the samples over the FULL frame (sum only)
     std::vector<const float4*> bufs(world);
@@ -381,9 +517,10 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
             RTB_CUDA(cudaMemsetAsync(g.d_rgba, 0, pixels * sizeof(float4), g.stream));
         } else {
             ViewDev vd = make_view(v, 0, 1, false);
-            rc = rtb_launch_trace(scene_dev(g, s->info.n_prims), vd, g.d_rgba, nullptr, nullptr, g.d_counters, g.stream,
-                                  &launches);
+            uint64_t primary = 0;
+            rc = launch_frame(g, g.lanes[0], s->info.n_prims, vd, g.d_rgba, nullptr, nullptr, g.stream, &launches, &primary);
             if (rc != RTB_OK) return rc;
+            primary_total += primary;
         }
         RTB_CUDA(cudaEventRecord(g.ev1, g.stream));
     }
@@ -421,6 +558,7 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
         st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
         st.ms_render = std::max(st.ms_render, (double)ms);
     }
+    st.rays += primary_total;
     st.ms_total = now_ms() - t0;
     st.kernel_launches = launches;
     st.n_gpus = world;

@@ -1,0 +1,168 @@
+// rtb_device.cuh — device-side building blocks shared by the megakernel (rtb_trace.cu) and the
+// wavefront pipeline (rtb_wavefront.cu): the exact f32 vector math, the RNG and the exact
+// ray/triangle test.
+//
+// Arithmetic contract: everything that feeds a value the reference also computes uses the explicit
+// round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn), which nvcc never
+// contracts into FMA, in the reference's operation order.  Reference: raytrace_lib/src/raytrace.rs.
+#pragma once
+
+#include <cfloat>
+
+#include "rtb_internal.cuh"
+
+namespace rtbdev {
+
+// ---------------------------------------------------------------------------
+// exact f32 vector math (raytrace.rs:35-96)
+// ---------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ V3 vmul(V3 a, float s) { return mk(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
+// dot = lane-wise product then ORDERED reduce over the 4 lanes of the reference's f32x4 (:66, :76):
+// ((p0 + p1) + p2) + p3 with p3 = 0*0.
+__device__ __forceinline__ float vdot(V3 a, V3 b) {
+    float s = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+    s = __fadd_rn(s, __fmul_rn(a.z, b.z));
+    return __fadd_rn(s, 0.0f);
+}
+__device__ __forceinline__ V3 vunit(V3 a) {   // :93-96: v * (1/len)
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(vdot(a, a)));
+    return vmul(a, inv);
+}
+
+// ---------------------------------------------------------------------------
+// RNG: pcg32 keyed by (seed, pixel, sample); floats as rand 0.8's Standard f32 (24-bit mantissa).
+// Same integer spec as oracle/rt_oracle.cpp so stochastic paths compare bit for bit.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct Rng {
+    uint64_t state;
+    __device__ __forceinline__ void seed(uint64_t seed, uint64_t pixel, uint32_t sample) {
+        uint64_t s = splitmix64(seed);
+        s = splitmix64(s ^ pixel);
+        s = splitmix64(s ^ (uint64_t)sample);
+        state = s;
+    }
+    __device__ __forceinline__ float next_f32() {
+        uint64_t old = state;
+        state = old * 6364136223846793005ull + 1442695040888963407ull;
+        uint32_t xorshifted = (uint32_t)(((old >> 18) ^ old) >> 27);
+        uint32_t rot = (uint32_t)(old >> 59);
+        uint32_t r = __funnelshift_r(xorshifted, xorshifted, rot);
+        return __fmul_rn((float)(r >> 8), 1.0f / 16777216.0f);
+    }
+};
+__device__ __forceinline__ V3 random_vec(Rng& g) {   // raytrace.rs:188-192
+    float a = __fsub_rn(g.next_f32(), 0.5f);
+    float b = __fsub_rn(g.next_f32(), 0.5f);
+    float c = __fsub_rn(g.next_f32(), 0.5f);
+    return vunit(mk(a, b, c));
+}
+
+// ---------------------------------------------------------------------------
+// Primary ray (Viewport::pixel_ray :1374-1394 + make_ray :201-210)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void gen_primary(const ViewDev& vw, uint32_t row, uint32_t col, float u_off, float v_off,
+                                            V3* o, V3* d) {
+    const V3 vu_delta = vmul(mk(vw.vu[0], vw.vu[1], vw.vu[2]), __fdiv_rn(1.0f, (float)vw.width));
+    const V3 vv_delta = vmul(mk(vw.vv[0], vw.vv[1], vw.vv[2]), __fdiv_rn(1.0f, (float)vw.height));
+    const V3 vu_frac = vmul(vu_delta, __fadd_rn((float)col, u_off));   // px = (row, col): px_y = col
+    const V3 vv_frac = vmul(vv_delta, __fadd_rn((float)row, v_off));
+    *o = vadd(vadd(mk(vw.orig[0], vw.orig[1], vw.orig[2]), vu_frac), vv_frac);
+    *d = vunit(vunit(vsub(*o, mk(vw.cam[0], vw.cam[1], vw.cam[2]))));  // unit() at :1393, again in make_ray
+}
+
+// ---------------------------------------------------------------------------
+// The acceptance part of Triangle::intersects (raytrace.rs:402-422) for one primitive.
+// Returns true and t when the reference would return Some(..).  `has`/`best` allow skipping work
+// that cannot change the running minimum (t > best can never win under strict-< / lowest-index).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool tri_test(const float4* __restrict__ q, V3 o, V3 d, bool has, float best, float* t_out) {
+    const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
+    const V3 n = mk(q0.x, q0.y, q0.z), c = mk(q1.x, q1.y, q1.z);
+    const float t = __fdiv_rn(vdot(n, vsub(c, o)), vdot(n, d));
+    if (t < 0.0f) return false;
+    if (has && t > best) return false;
+    const V3 ip = vsub(vadd(vmul(d, t), o), c);
+    if (vdot(ip, ip) > q0.w) return false;
+    const float4 q2 = __ldg(q + 2);
+    if (vdot(ip, mk(q2.x, q2.y, q2.z)) > q2.w) return false;
+    const float4 q3 = __ldg(q + 3);
+    if (vdot(ip, mk(q3.x, q3.y, q3.z)) > q3.w) return false;
+    const float4 q4 = __ldg(q + 4);
+    if (vdot(ip, mk(q4.x, q4.y, q4.z)) > q4.w) return false;
+    *t_out = t;
+    return true;
+}
+
+struct Hit {
+    float t;
+    int slot;        // leaf-order primitive slot, -1 = miss
+    uint32_t orig;   // original triangle index of `slot`
+};
+
+// Surface response at a hit (Triangle::intersects :406-436 recomputed for the winner, getsurface :450-459,
+// normal :441-449, color_ray :1228-1252).  Returns:
+//   0 = terminal, *color is the path's terminal colour (edge -> black, Solid -> colour)
+//   1 = bounce: *color/*alpha go on the mix stack, (*no, *nd) is the next ray
+__device__ __forceinline__ int shade_hit(const SceneDev& sc, int slot, float t, V3 o, V3 d, Rng& g, V3* color,
+                                         float* alpha, V3* no, V3* nd) {
+    const float4* q = sc.tri + (size_t)RTB_TRI_F4 * (uint32_t)slot;
+    const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
+    const float4 s0 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)slot);
+    const float4 s1 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)slot + 1);
+    const V3 n = mk(q0.x, q0.y, q0.z);
+    const V3 p = vadd(vmul(d, t), o);
+    const V3 ip = vsub(p, mk(q1.x, q1.y, q1.z));
+    const float edge_k = __fsub_rn(1.0f, s1.z);
+    bool hit_edge = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float4 qs = __ldg(q + 2 + i);
+        const float dist = vdot(ip, mk(qs.x, qs.y, qs.z));
+        if (dist > __fmul_rn(qs.w, edge_k)) hit_edge = true;
+    }
+    if (hit_edge) { *color = mk(0.0f, 0.0f, 0.0f); return 0; }
+    const uint32_t kind = __float_as_uint(s1.x);
+    *color = mk(s0.x, s0.y, s0.z);
+    if (kind == RTB_SOLID) return 0;
+    *alpha = s0.w;
+    const bool back = vdot(d, n) > 0.0f;                     // :425-435
+    const V3 nn = back ? vmul(n, -1.0f) : n;
+    if (kind == RTB_MATTE) {                                 // lambertian_ray :292-297
+        const V3 rv = random_vec(g);
+        *no = vadd(p, vmul(rv, 0.001f));
+        *nd = vunit(vadd(nn, rv));
+    } else {                                                 // reflect_ray :278-290
+        const float ddot = fabsf(vdot(d, nn));
+        const V3 dir_p = vmul(nn, ddot);
+        const V3 dir_o = vadd(d, dir_p);
+        const V3 reflect = vadd(dir_p, dir_o);
+        const V3 rv = vmul(random_vec(g), s1.y);
+        const V3 rd = vunit(vadd(reflect, rv));
+        *no = vadd(p, vmul(rd, 0.001f));
+        *nd = vunit(rd);                                     // make_ray normalises again
+    }
+    return 1;
+}
+
+// mix_color(c, sub, a) = c*(1-a) + sub*a  (:299-301)
+__device__ __forceinline__ V3 mix_color(V3 c, V3 sub, float a) {
+    return vadd(vmul(c, __fsub_rn(1.0f, a)), vmul(sub, a));
+}
+
+__device__ __forceinline__ V3 sky_color() {   // make_color((128,180,255)) :1264
+    return mk(__fdiv_rn(128.0f, 255.0f), __fdiv_rn(180.0f, 255.0f), __fdiv_rn(255.0f, 255.0f));
+}
+
+}  // namespace rtbdev

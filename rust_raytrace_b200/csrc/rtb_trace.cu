@@ -15,95 +15,11 @@
 // explicit round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn), which
 // nvcc never contracts into FMA, in the reference's operation order (dot = ((p0+p1)+p2)+0).
 // Only the AABB slab test, which has no counterpart in the reference's result, is free-form.
-#include <cfloat>
+#include "rtb_device.cuh"
 
-#include "rtb_internal.cuh"
+using namespace rtbdev;
 
 namespace {
-
-// ---------------------------------------------------------------------------
-// exact f32 vector math (raytrace.rs:35-96)
-// ---------------------------------------------------------------------------
-struct V3 { float x, y, z; };
-
-__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
-__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
-__device__ __forceinline__ V3 vmul(V3 a, float s) { return mk(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
-__device__ __forceinline__ float vdot(V3 a, V3 b) {
-    float s = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
-    s = __fadd_rn(s, __fmul_rn(a.z, b.z));
-    return __fadd_rn(s, 0.0f);   // lane 3 of the reference's f32x4 (0*0)
-}
-__device__ __forceinline__ V3 vunit(V3 a) {
-    float inv = __fdiv_rn(1.0f, __fsqrt_rn(vdot(a, a)));
-    return vmul(a, inv);
-}
-
-// ---------------------------------------------------------------------------
-// RNG: pcg32 keyed by (seed, pixel, sample); floats as rand 0.8's Standard f32.
-// Same integer spec as oracle/rt_oracle.cpp so stochastic paths compare bit for bit.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    uint64_t z = x;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-struct Rng {
-    uint64_t state;
-    __device__ __forceinline__ void seed(uint64_t seed, uint64_t pixel, uint32_t sample) {
-        uint64_t s = splitmix64(seed);
-        s = splitmix64(s ^ pixel);
-        s = splitmix64(s ^ (uint64_t)sample);
-        state = s;
-    }
-    __device__ __forceinline__ float next_f32() {
-        uint64_t old = state;
-        state = old * 6364136223846793005ull + 1442695040888963407ull;
-        uint32_t xorshifted = (uint32_t)(((old >> 18) ^ old) >> 27);
-        uint32_t rot = (uint32_t)(old >> 59);
-        uint32_t r = __funnelshift_r(xorshifted, xorshifted, rot);
-        return __fmul_rn((float)(r >> 8), 1.0f / 16777216.0f);
-    }
-};
-__device__ __forceinline__ V3 random_vec(Rng& g) {   // raytrace.rs:188-192
-    float a = __fsub_rn(g.next_f32(), 0.5f);
-    float b = __fsub_rn(g.next_f32(), 0.5f);
-    float c = __fsub_rn(g.next_f32(), 0.5f);
-    return vunit(mk(a, b, c));
-}
-
-// ---------------------------------------------------------------------------
-// closest hit
-// ---------------------------------------------------------------------------
-struct Hit {
-    float t;
-    int slot;        // leaf-order primitive slot, -1 = miss
-    uint32_t orig;   // original triangle index of `slot`
-};
-
-// The acceptance part of Triangle::intersects (raytrace.rs:402-422) for one primitive.
-// Returns true and t when the reference would return Some(..).  `has`/`best` allow skipping work
-// that cannot change the running minimum (t > best can never win under strict-< / lowest-index).
-__device__ __forceinline__ bool tri_test(const float4* __restrict__ q, V3 o, V3 d, bool has, float best, float* t_out) {
-    const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
-    const V3 n = mk(q0.x, q0.y, q0.z), c = mk(q1.x, q1.y, q1.z);
-    const float t = __fdiv_rn(vdot(n, vsub(c, o)), vdot(n, d));
-    if (t < 0.0f) return false;
-    if (has && t > best) return false;
-    const V3 ip = vsub(vadd(vmul(d, t), o), c);
-    if (vdot(ip, ip) > q0.w) return false;
-    const float4 q2 = __ldg(q + 2);
-    if (vdot(ip, mk(q2.x, q2.y, q2.z)) > q2.w) return false;
-    const float4 q3 = __ldg(q + 3);
-    if (vdot(ip, mk(q3.x, q3.y, q3.z)) > q3.w) return false;
-    const float4 q4 = __ldg(q + 4);
-    if (vdot(ip, mk(q4.x, q4.y, q4.z)) > q4.w) return false;
-    *t_out = t;
-    return true;
-}
 
 template <bool STATS>
 __device__ __forceinline__ Hit closest_hit(const SceneDev& sc, V3 o, V3 d, bool brute, unsigned long long& n_node,
@@ -220,7 +136,8 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
                                                TraceCounters* __restrict__ counters) {
     // tile -> pixel mapping: block = 16x8 pixels, warp = 8x4 pixels
     const uint32_t tile = blockIdx.x;
-    const uint32_t my_ty = tile / vw.tiles_x, tx = tile - my_ty * vw.tiles_x;
+    const uint32_t ty_local = tile / vw.tiles_x, tx = tile - ty_local * vw.tiles_x;
+    const uint32_t my_ty = ty_local + vw.band_begin;
     const uint32_t ty = my_ty * vw.tile_world + vw.tile_rank;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
@@ -230,12 +147,7 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
     unsigned long long n_rays = 0, n_node = 0, n_tri = 0;
 
     if (active) {
-        const V3 v_orig = mk(vw.orig[0], vw.orig[1], vw.orig[2]);
-        const V3 v_cam = mk(vw.cam[0], vw.cam[1], vw.cam[2]);
-        // pixel_ray :1379-1380
-        const V3 vu_delta = vmul(mk(vw.vu[0], vw.vu[1], vw.vu[2]), __fdiv_rn(1.0f, (float)vw.width));
-        const V3 vv_delta = vmul(mk(vw.vv[0], vw.vv[1], vw.vv[2]), __fdiv_rn(1.0f, (float)vw.height));
-        const V3 blue = mk(__fdiv_rn(128.0f, 255.0f), __fdiv_rn(180.0f, 255.0f), __fdiv_rn(255.0f, 255.0f));
+        const V3 blue = sky_color();
         const uint64_t pix = (uint64_t)row * vw.width + col;
 
         V3 acc = mk(0.0f, 0.0f, 0.0f);
@@ -247,11 +159,8 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
             g.seed(vw.seed, pix, smp);
             float u_off = 0.5f, v_off = 0.5f;
             if (vw.spp != 1) { u_off = g.next_f32(); v_off = g.next_f32(); }
-            // pixel_ray :1388-1393 (px = (row, col): px_x = row, px_y = col)
-            const V3 vu_frac = vmul(vu_delta, __fadd_rn((float)col, u_off));
-            const V3 vv_frac = vmul(vv_delta, __fadd_rn((float)row, v_off));
-            V3 o = vadd(vadd(v_orig, vu_frac), vv_frac);
-            V3 d = vunit(vunit(vsub(o, v_cam)));   // unit() at :1393, again inside make_ray :202
+            V3 o, d;
+            gen_primary(vw, row, col, u_off, v_off, &o, &d);
 
             V3 cstack[RTB_MAX_DEPTH];
             float astack[RTB_MAX_DEPTH];
@@ -264,45 +173,11 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
                 const Hit h = closest_hit<STATS>(sc, o, d, (vw.flags & RTB_FLAG_BRUTE) != 0u, n_node, n_tri);
                 if (level == 0 && smp == 0) { first_prim = h.slot >= 0 ? h.orig : 0u; first_t = h.slot >= 0 ? h.t : 0.0f; }
                 if (h.slot < 0) { term = blue; break; }
-                // classify the hit: Triangle::intersects :406-436 recomputed for the winner
-                const float4* q = sc.tri + (size_t)RTB_TRI_F4 * (uint32_t)h.slot;
-                const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
-                const float4 s0 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)h.slot);
-                const float4 s1 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)h.slot + 1);
-                const V3 n = mk(q0.x, q0.y, q0.z);
-                const V3 p = vadd(vmul(d, h.t), o);
-                const V3 ip = vsub(p, mk(q1.x, q1.y, q1.z));
-                const float edge_k = __fsub_rn(1.0f, s1.z);
-                bool hit_edge = false;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float4 qs = __ldg(q + 2 + i);
-                    const float dist = vdot(ip, mk(qs.x, qs.y, qs.z));
-                    if (dist > __fmul_rn(qs.w, edge_k)) hit_edge = true;
-                }
-                if (hit_edge) { term = mk(0.0f, 0.0f, 0.0f); break; }   // getsurface :450-459
-                const uint32_t kind = __float_as_uint(s1.x);
-                const V3 color = mk(s0.x, s0.y, s0.z);
-                if (kind == RTB_SOLID) { term = color; break; }
-                const bool back = vdot(d, n) > 0.0f;                     // :425-435
-                const V3 nn = back ? vmul(n, -1.0f) : n;                 // normal() :441-449
-                V3 no, nd;
-                if (kind == RTB_MATTE) {                                 // lambertian_ray :292-297
-                    const V3 rv = random_vec(g);
-                    no = vadd(p, vmul(rv, 0.001f));
-                    nd = vunit(vadd(nn, rv));
-                } else {                                                 // reflect_ray :278-290
-                    const float ddot = fabsf(vdot(d, nn));
-                    const V3 dir_p = vmul(nn, ddot);
-                    const V3 dir_o = vadd(d, dir_p);
-                    const V3 reflect = vadd(dir_p, dir_o);
-                    const V3 rv = vmul(random_vec(g), s1.y);
-                    const V3 rd = vunit(vadd(reflect, rv));
-                    no = vadd(p, vmul(rd, 0.001f));
-                    nd = vunit(rd);                                      // make_ray normalises again
-                }
+                V3 color, no, nd;
+                float alpha = 0.0f;
+                if (shade_hit(sc, h.slot, h.t, o, d, g, &color, &alpha, &no, &nd) == 0) { term = color; break; }
                 cstack[level] = color;
-                astack[level] = s0.w;
+                astack[level] = alpha;
                 ++level;
                 --depth;
                 if (depth == 0) { term = mk(0.0f, 0.0f, 0.0f); break; }  // project_ray(depth 0): black, not counted
@@ -310,8 +185,7 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
             }
             // unwind the recursion: mix_color(c, sub, a) = c*(1-a) + sub*a  (:299-301), innermost first
             V3 cres = term;
-            for (int k = level - 1; k >= 0; --k)
-                cres = vadd(vmul(cstack[k], __fsub_rn(1.0f, astack[k])), vmul(cres, astack[k]));
+            for (int k = level - 1; k >= 0; --k) cres = mix_color(cstack[k], cres, astack[k]);
             acc = vadd(acc, cres);
         }
         if (!(vw.flags & RTB_FLAG_SUM_ONLY)) acc = vmul(acc, __fdiv_rn(1.0f, (float)vw.spp));   // :1426

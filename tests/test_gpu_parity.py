@@ -138,6 +138,22 @@ def test_bvh_equals_gpu_bruteforce(R, scenes):
     assert a[3].total_rays == b[3].total_rays
 
 
+@pytest.mark.parametrize("spp", [1, 3])
+def test_megakernel_equals_wavefront(R, O, scenes, spp):
+    """The two renderers in the library (default wavefront pipeline, RTB_FLAG_MEGAKERNEL) are the same
+    function: ids, t, colour and ray count, including multi-sample accumulation order."""
+    from rust_raytrace_b200 import _lib
+    s, _, bvh = scenes[False]
+    v = R.main_viewport(801, 453, 5, spp)
+    a = gpu_render(R, s, v, seed=13)
+    vm = _lib.RtbView.from_buffer_copy(v)
+    vm.flags |= _lib.RTB_FLAG_MEGAKERNEL
+    b = gpu_render(R, s, vm, seed=13)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+    assert a[3].total_rays == b[3].total_rays
+    assert_bit_exact(b, bvh.render(O.main_viewport(801, 453, 5, spp), seed=13), f"megakernel spp={spp}")
+
+
 def test_rotated_camera(R, O, scenes):
     s, _, bvh = scenes[True]
     args = ((400, 300), (1.0, 0.75), [1.0, -1.0, 0.5], None, 60.0, 0.4, 5, 1)
