@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librtb.so")
+LIB_PATH = os.environ.get("RTB_LIB", os.path.join(_PKG, "librtb.so"))   # RTB_LIB: A/B builds of the same ABI
 
 RTB_OK, RTB_ERR_NO_DEVICE, RTB_ERR_CUDA, RTB_ERR_INVALID, RTB_ERR_NOMEM = 0, -1, -2, -3, -4
 RTB_SOLID, RTB_MATTE, RTB_REFLECTIVE = 0, 1, 2

@@ -48,7 +48,7 @@ void free_gpu_scene(GpuScene& g) {
     if (g.device < 0) return;
     cudaSetDevice(g.device);
     if (g.stream) cudaStreamSynchronize(g.stream);
-    cudaFree(g.d_nodes); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
+    cudaFree(g.d_nodes); cudaFree(g.d_nodes4); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
     cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t);
     for (auto& l : g.lanes) {
         cudaFree(l.d_ws);
@@ -109,6 +109,8 @@ SceneDev scene_dev(const GpuScene& g, uint32_t n_prims) {
     SceneDev s;
     s.nodes = g.d_nodes; s.tri = g.d_tri; s.shade = g.d_shade; s.n_prims = n_prims; s.n_nodes = g.n_nodes;
     s.height = g.height;
+    s.nodes4 = g.d_nodes4;
+    s.stack4 = 3u * (g.depth4 + 1u) + 2u;
     return s;
 }
 
@@ -161,7 +163,13 @@ int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d
     for (uint32_t l = 0; l < n_lanes; ++l) {
         GpuLane& lane = g.lanes[l];
         if (!lane.done) RTB_CUDA(cudaEventCreateWithFlags(&lane.done, cudaEventDisableTiming));
-        if (l > 0 && !lane.st) RTB_CUDA(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
+        if (l > 0 && !lane.st) {
+            // later lanes get lower priority: earlier pieces then finish first and their D2H copies start while
+            // the later pieces still render (equal priorities made all pieces finish together)
+            int lo = 0, hi = 0;
+            RTB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least (numerically largest)
+            RTB_CUDA(cudaStreamCreateWithPriority(&lane.st, cudaStreamNonBlocking, std::min(lo, hi + (int)l)));
+        }
     }
     if (n_lanes > 1) {
         if (!g.fork_ev) RTB_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
@@ -268,8 +276,12 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
         auto bail = [&](int code) { for (auto& x : s->gpu) free_gpu_scene(x); delete s; return code; };
         cudaError_t e;
         if ((e = cudaSetDevice(g.device)) != cudaSuccess) return bail(rtb_cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__));
-        if ((e = cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking)) != cudaSuccess)
-            return bail(rtb_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+        {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if ((e = cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, hi)) != cudaSuccess)
+                return bail(rtb_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+        }
         cudaEventCreate(&g.ev0);
         cudaEventCreate(&g.ev1);
         if ((e = cudaMalloc(&g.d_counters, sizeof(TraceCounters))) != cudaSuccess)
@@ -296,6 +308,7 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
         g.d_nodes = br.d_nodes; g.d_tri = br.d_tri; g.d_shade = br.d_shade; g.d_prim_order = br.d_prim_order;
         g.n_nodes = br.n_nodes;
         g.height = br.tree_height;
+        g.d_nodes4 = br.d_nodes4; g.n_nodes4 = br.n_nodes4; g.depth4 = br.depth4;
         if (rc != RTB_OK) return bail(rc);
         if (gi == 0) {
             s->info.n_nodes = br.n_nodes; s->info.n_leaves = br.n_leaves; s->info.max_leaf = br.max_leaf;

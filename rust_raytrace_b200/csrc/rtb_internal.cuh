@@ -34,6 +34,8 @@ struct SceneDev {
     uint32_t n_prims;
     uint32_t n_nodes;
     uint32_t height;     // tree height: the traversal stack never holds more than `height` entries
+    const float4* nodes4;   // 4-wide collapse of the same tree: 8 x float4 (128 B) per node, see rtb_lbvh.cu
+    uint32_t stack4;     // stack entries a BVH4 traversal can need: 3 per level
 };
 
 #define RTB_TRI_F4 5
@@ -42,10 +44,11 @@ struct SceneDev {
 #define RTB_STACK 64
 #define RTB_MAX_CHUNKS 16
 #define RTB_MAX_LANES 4
-// Measured on B200 (4K teapot frame, ms per frame; pieces/lanes): device-resident output 1/1 3.05, 2/2 2.71, 4/4 2.69,
-// 8/4 3.19, 16/4 4.66; host output incl. D2H 1/1 5.49, 4/2 4.51, 8/4 4.45, 16/4 5.44.
+// Measured on B200 (4K teapot frame, ms per frame; pieces/lanes), raygen + trace + shade + bounce pipeline:
+// device-resident output 1/1 3.12, 2/2 3.12, 4/4 3.39, 8/4 3.46; host output incl. the 133 MB D2H (2.34 ms alone)
+// 1/1 5.56, 2/2 4.81, 4/4 4.14, 6/3 4.00, 8/4 4.00.
 #define RTB_DEFAULT_PIECES 8          /* rtb_render: more pieces = earlier D2H overlap */
-#define RTB_DEFAULT_PIECES_DEVICE 4   /* rtb_render_device: no copies to overlap */
+#define RTB_DEFAULT_PIECES_DEVICE 1   /* rtb_render_device: no copies to overlap */
 #define RTB_DEFAULT_LANES 4
 
 // Image tiling: one CTA = 128 threads = 16 x 8 pixels; one warp = 8 x 4 pixels.
@@ -100,6 +103,8 @@ struct GpuScene {
     size_t fb_pixels = 0;
     uint32_t n_nodes = 0;
     uint32_t height = 0;
+    float4* d_nodes4 = nullptr;
+    uint32_t n_nodes4 = 0, depth4 = 0;
     GpuLane lanes[RTB_MAX_LANES];
     cudaEvent_t fork_ev = nullptr;
 };
@@ -126,6 +131,8 @@ struct BuildResult {
     float4* d_shade = nullptr;
     uint32_t* d_prim_order = nullptr;
     uint32_t n_nodes = 0, n_leaves = 0, max_leaf = 0, tree_height = 0;
+    float4* d_nodes4 = nullptr;      // 4-wide collapse, 8 x float4 per node
+    uint32_t n_nodes4 = 0, depth4 = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     float ms_build = 0.f;
     uint32_t launches = 0;

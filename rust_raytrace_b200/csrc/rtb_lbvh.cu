@@ -37,12 +37,13 @@ struct BuildScratch {
     uint32_t height;        // tree height (edges from the root to the deepest Karras leaf)
     uint32_t max_leaf;
     uint32_t n_leaves;
+    uint32_t depth4;        // depth of the deepest 4-wide node (root = 0)
 };
 
 __global__ void k_init_scratch(BuildScratch* s) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         for (int k = 0; k < 3; ++k) { s->scene_lo[k] = 0xffffffffu; s->scene_hi[k] = 0u; }
-        s->max_abs = 0u; s->height = 0u; s->max_leaf = 0u; s->n_leaves = 0u;
+        s->max_abs = 0u; s->height = 0u; s->max_leaf = 0u; s->n_leaves = 0u; s->depth4 = 0u;
     }
 }
 
@@ -226,6 +227,76 @@ __global__ void k_emit_nodes(int n, const int2* __restrict__ children, const int
     }
 }
 
+// ---- 4-wide collapse -------------------------------------------------------------------------------
+// A BVH4 node is rooted at the root and at every internal node that covers more than RTB_LEAF_MAX primitives
+// and sits at EVEN depth of the binary tree; its (up to 4) entries are its grandchildren, or a child
+// itself where that child is already a leaf.  Node = 8 x float4 (128 B, one cache line), SoA over the
+// entries: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] code[4] pad.  code: 0 = empty slot,
+// 0x80000000 | first<<3 | count = leaf, otherwise the index of the child BVH4 node.
+__global__ void k_flag4(int n_internal, const int2* __restrict__ range, const int* __restrict__ parent,
+                        uint32_t* __restrict__ flags4, BuildScratch* s) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    uint32_t depth = 0;
+    for (int p = parent[i]; p >= 0; p = parent[p]) ++depth;
+    const int size = range[i].y - range[i].x + 1;
+    const bool kept = (i == 0) || (size > RTB_LEAF_MAX && (depth & 1u) == 0u);
+    flags4[i] = kept ? 1u : 0u;
+    if (kept) atomicMax(&s->depth4, depth >> 1);
+}
+
+__global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const int2* __restrict__ range,
+                              const float4* __restrict__ blo, const float4* __restrict__ bhi,
+                              const uint32_t* __restrict__ flags4, const uint32_t* __restrict__ idx4,
+                              float4* __restrict__ nodes4, const BuildScratch* __restrict__ s) {
+    const int n_internal = n - 1;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_internal > 0 ? n_internal : 1)) return;
+    if (n_internal > 0 && !flags4[i]) return;
+    const float pad = o2f(s->max_abs) * (1.0f / 131072.0f);
+    auto leaf_final = [&](int c) { return c >= n - 1 || (range[c].y - range[c].x + 1) <= RTB_LEAF_MAX; };
+    int ent[4];
+    int n_ent = 0;
+    if (n_internal == 0) ent[n_ent++] = 0;                       // the single Karras leaf
+    else if (leaf_final(i)) ent[n_ent++] = i;                    // tiny scene: the root itself is a leaf
+    else {
+        const int2 ch = children[i];
+        const int cs[2] = {ch.x, ch.y};
+        for (int k = 0; k < 2; ++k) {
+            if (leaf_final(cs[k])) ent[n_ent++] = cs[k];
+            else { const int2 g = children[cs[k]]; ent[n_ent++] = g.x; ent[n_ent++] = g.y; }
+        }
+    }
+    float lo[3][4], hi[3][4];
+    uint32_t code[4];
+    for (int e = 0; e < 4; ++e) {
+        if (e < n_ent) {
+            const int c = ent[e];
+            const float4 l = blo[c], h = bhi[c];
+            lo[0][e] = l.x - pad; lo[1][e] = l.y - pad; lo[2][e] = l.z - pad;
+            hi[0][e] = h.x + pad; hi[1][e] = h.y + pad; hi[2][e] = h.z + pad;
+            if (leaf_final(c)) {
+                const uint32_t first = c >= n - 1 ? (uint32_t)(c - (n - 1)) : (uint32_t)range[c].x;
+                const uint32_t cnt = c >= n - 1 ? 1u : (uint32_t)(range[c].y - range[c].x + 1);
+                code[e] = 0x80000000u | (first << 3) | cnt;
+            } else {
+                code[e] = idx4[c];
+            }
+        } else {
+            lo[0][e] = lo[1][e] = lo[2][e] = 1e30f;
+            hi[0][e] = hi[1][e] = hi[2][e] = -1e30f;
+            code[e] = 0u;
+        }
+    }
+    float4* out = nodes4 + 8u * (n_internal > 0 ? idx4[i] : 0u);
+    for (int a = 0; a < 3; ++a) {
+        out[2 * a + 0] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        out[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+    out[6] = make_float4(__uint_as_float(code[0]), __uint_as_float(code[1]), __uint_as_float(code[2]), __uint_as_float(code[3]));
+    out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void k_emit_tris(const RtbTriangle* __restrict__ tris, const uint32_t* __restrict__ keep,
                             const uint32_t* __restrict__ sorted_vals, uint32_t n, float4* __restrict__ tri,
                             float4* __restrict__ shade, uint32_t* __restrict__ prim_order) {
@@ -276,6 +347,10 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
         RTB_CUDA(cudaMemcpyAsync(out->d_nodes, h, sizeof h, cudaMemcpyHostToDevice, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
         out->n_nodes = 2;
+        RTB_CUDA(cudaMalloc(&out->d_nodes4, sizeof(float4) * 8));
+        RTB_CUDA(cudaMemsetAsync(out->d_nodes4, 0, sizeof(float4) * 8, stream));   // all codes 0 = empty
+        RTB_CUDA(cudaStreamSynchronize(stream));
+        out->n_nodes4 = 1;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return RTB_OK;
     }
@@ -283,7 +358,7 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     DevBuf<BuildScratch> scratch;
     DevBuf<float4> plo, phi, blo, bhi;
     DevBuf<uint64_t> keys, keys_sorted;
-    DevBuf<uint32_t> vals, vals_sorted, arrive, flags, slot;
+    DevBuf<uint32_t> vals, vals_sorted, arrive, flags, slot, flags4, idx4;
     DevBuf<int2> children, range;
     DevBuf<int> parent;
     DevBuf<uint8_t> cub_tmp;
@@ -295,6 +370,7 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     RTB_CUDA(vals.alloc(n)); RTB_CUDA(vals_sorted.alloc(n));
     RTB_CUDA(arrive.alloc(n_int)); RTB_CUDA(flags.alloc(n_int + 1)); RTB_CUDA(slot.alloc(n_int + 1));
     RTB_CUDA(children.alloc(n_int)); RTB_CUDA(range.alloc(n_int)); RTB_CUDA(parent.alloc(n_all));
+    RTB_CUDA(flags4.alloc(n_int + 1)); RTB_CUDA(idx4.alloc(n_int + 1));
 
     size_t sort_bytes = 0, scan_bytes = 0;
     RTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n,
@@ -337,6 +413,20 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
                                                    out->d_nodes, scratch.p); ++launches;
     k_emit_tris<<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, vals_sorted.p, n, out->d_tri, out->d_shade,
                                               out->d_prim_order); ++launches;
+    // 4-wide collapse of the same tree (used by the wavefront renderer)
+    uint32_t total4 = 1;
+    if (n_int > 0) {
+        k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, range.p, parent.p, flags4.p, scratch.p); ++launches;
+        RTB_CUDA(cudaMemsetAsync(flags4.p + n_int, 0, sizeof(uint32_t), stream));
+        RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, flags4.p, idx4.p, (int)(n_int + 1), stream));
+        launches += 1;
+        RTB_CUDA(cudaMemcpyAsync(&total4, idx4.p + n_int, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        RTB_CUDA(cudaStreamSynchronize(stream));
+    }
+    out->n_nodes4 = total4;
+    RTB_CUDA(cudaMalloc(&out->d_nodes4, sizeof(float4) * 8 * (size_t)total4));
+    k_emit_nodes4<<<cdiv(n_int > 0 ? n_int : 1, B), B, 0, stream>>>((int)n, children.p, range.p, blo.p, bhi.p, flags4.p,
+                                                                  idx4.p, out->d_nodes4, scratch.p); ++launches;
     RTB_CUDA(cudaEventRecord(e1, stream));
     BuildScratch h;
     RTB_CUDA(cudaMemcpyAsync(&h, scratch.p, sizeof h, cudaMemcpyDeviceToHost, stream));
@@ -348,6 +438,7 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     auto dec = [](uint32_t o) { uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; float f; memcpy(&f, &u, 4); return f; };
     for (int k = 0; k < 3; ++k) { out->lo[k] = dec(h.scene_lo[k]); out->hi[k] = dec(h.scene_hi[k]); }
     out->tree_height = h.height;
+    out->depth4 = h.depth4;
     out->max_leaf = h.max_leaf;
     out->n_leaves = h.n_leaves;
     out->launches = launches;

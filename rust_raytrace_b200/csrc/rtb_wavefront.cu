@@ -2,21 +2,23 @@
 //
 // The one-kernel version (rtb_trace.cu) keeps only ~9 of 32 lanes busy per issued instruction
 // (ncu, profiles/r1_v1_*): rays of one warp leave the scene at different times and the surviving
-// Matte/mirror paths bounce up to maxdepth times.  Here the same arithmetic is split into stages that
-// each run with full warps:
+// Matte/mirror paths bounce up to maxdepth times.  Here the same arithmetic is split into stages:
 //
 //   k_wf_raygen   one thread per pixel slot: Viewport::pixel_ray (raytrace.rs:1374-1394) -> ray queue 0
-//   k_wf_trace    PERSISTENT kernel: warps pull rays from the level's queue, every lane that finishes its
-//                 ray is refilled from the queue (ballot + one atomic per 128 rays per warp), so the
-//                 traversal loop runs with (almost) all 32 lanes; closest hit -> hit record
-//   k_wf_shade    one thread per ray: Triangle::intersects classification, color_ray (:1199-1254):
-//                 terminal paths fold their mix_color stack innermost-first and add the sample to the
-//                 pixel; bouncing paths push (colour, alpha) and append the next ray to the next queue
-//                 (warp-aggregated atomic = stream compaction)
-//   k_wf_tally    per-sample counter roll-up / reset
+//   k_wf_trace    PERSISTENT kernel over the coherent primary rays: warps pull rays from the queue, every
+//                 lane that finishes its ray is refilled (ballot + one atomic per 128 rays per warp), so the
+//                 traversal loop runs with ~25 of 32 lanes; closest hit -> hit record
+//   k_wf_shade    one thread per primary ray: Triangle::intersects classification, color_ray (:1199-1254):
+//                 terminal paths add their sample to the pixel; bouncing paths push (colour, alpha) on the
+//                 pixel's mix stack and append the bounce ray to the bounce queue (warp-aggregated atomic)
+//   k_wf_bounce   PERSISTENT kernel that takes every bounce path to its end: trace, shade, bounce again in
+//                 place (project_ray's recursion, iteratively), refilling a lane from the bounce queue only
+//                 when its path dies.  A first version ran one trace + one shade kernel per bounce level;
+//                 every level then paid its own drain (a few 100-step rays keep a few warps alive, >= ~0.15 ms
+//                 per level however few rays it holds) and ran with 9-16 of 32 lanes.
+//   k_wf_tally    per-sample counter reset
 //
-// Per-pixel state lives in HBM between stages (ray 32 B, hit 8 B, mix stack 16 B/level, RNG 8 B); at 4K
-// that is ~0.7 GB of traffic per frame, i.e. ~0.1 ms at the measured 6.5 TB/s.
+// Per-pixel state lives in HBM between stages (ray 32 B, hit 8 B, mix stack 16 B/level, RNG 8 B).
 #include <algorithm>
 #include <cstdlib>
 
@@ -30,14 +32,18 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t INVALID_SLOT = 0xffffffffu;
 constexpr uint32_t LEAF_FLAG = 0x80000000u;
 constexpr uint32_t WF_CHUNK = 128;      // rays reserved per warp per global atomic
-constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent trace kernel
-// Tunables (env RTB_WF_DESCEND / RTB_WF_REFILL override for experiments).  Measured on B200, 4K teapot frame:
-// (descend, refill) = (2,4) 3.53 ms, (4,8) 3.15 ms, (8,16) 3.06 ms, (unbounded,16) 3.30 ms.  Retiring surplus warps
-// on small queues made things worse in proportion (the deep levels are latency-, not issue-bound).
-constexpr uint32_t WF_DESCEND_MAX = 8;  // internal-node steps per lane per round before leaves are processed
-constexpr uint32_t WF_REFILL_MIN = 16;   // refill idle lanes once at least this many are idle
+constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent kernels
+#ifndef WF_BOUNCE_MIN_BLOCKS
+#define WF_BOUNCE_MIN_BLOCKS 8          // 64 registers: 32 warps/SM instead of 24 at the natural 80
+#endif
+// Tunables (env RTB_WF_DESCEND / RTB_WF_REFILL override for experiments).  Measured on B200, 4K teapot frame, with
+// one trace kernel per bounce level: (descend, refill) = (2,4) 3.53 ms, (4,8) 3.15 ms, (8,16) 3.06 ms,
+// (unbounded,16) 3.30 ms.  Retiring surplus warps on small queues made things worse in proportion (the deep
+// levels are latency-, not issue-bound).
+constexpr uint32_t WF_DESCEND_MAX = 4;  // BVH4 node visits per lane per round before leaves are processed
+constexpr uint32_t WF_REFILL_MIN = 16;  // service (shade / refill) lanes once at least this many wait
 
-// slot -> pixel.  Slots enumerate 8x4 warp tiles inside the 8-row bands this rank owns.
+// slot -> pixel.  Slots enumerate 8x4 warp tiles inside the 8-row bands this launch renders.
 struct Pixel { uint32_t row, col, out_idx; bool inside; };
 __device__ __forceinline__ Pixel slot_to_pixel(const ViewDev& vw, uint32_t slot) {
     const uint32_t wt = slot >> 5, l = slot & 31u;
@@ -81,185 +87,200 @@ __global__ void __launch_bounds__(256) k_wf_raygen(const ViewDev vw, uint32_t sm
 }
 
 // ---------------------------------------------------------------------------
-// stage 1: closest hit, persistent threads with per-lane refill
+// traversal machinery shared by the two persistent kernels
 // ---------------------------------------------------------------------------
 struct TravState {
     V3 o, d;
     float ix, iy, iz, ox, oy, oz;
     float tbest;
     Hit h;
-    uint32_t cur;      // LEAF_FLAG | first<<3 | count, or the left node index of an internal sibling pair
+    uint32_t cur;      // LEAF_FLAG | first<<3 | count, or the index of a BVH4 node
     int sp;
 };
 
+__device__ __forceinline__ uint32_t root_code_of(const SceneDev&) {
+    return 0u;   // BVH4 node 0 (an empty scene has one node whose four slots are all empty)
+}
+
+__device__ __forceinline__ void start_ray(TravState& s, V3 o, V3 d, uint32_t root_code) {
+    s.o = o; s.d = d;
+    // |1/d| clamped so a zero direction component gives +-huge, not inf (inf - inf = NaN in the fused slab test)
+    s.ix = fminf(fmaxf(1.0f / d.x, -1e30f), 1e30f);
+    s.iy = fminf(fmaxf(1.0f / d.y, -1e30f), 1e30f);
+    s.iz = fminf(fmaxf(1.0f / d.z, -1e30f), 1e30f);
+    s.ox = -o.x * s.ix; s.oy = -o.y * s.iy; s.oz = -o.z * s.iz;
+    s.tbest = FLT_MAX;
+    s.h.t = FLT_MAX; s.h.slot = -1; s.h.orig = 0xffffffffu;
+    s.sp = 0;
+    s.cur = root_code;
+}
+
+// One traversal round for the lanes with trav == true; every lane of the warp must call it.
+//   phase 1: at most `k_nodes` BVH4 node visits (unbounded descent, the classic while-while, left lanes that had
+//            reached a leaf waiting for the slowest lane of the warp)
+//   phase 2: the leaf this lane holds, if it reached one
+// trav becomes false when the lane's ray is finished (result in s.h).  The stack lives in SHARED memory, one
+// 4-byte code per entry, [depth][thread]: as thread-local arrays the stacks went through L1 and evicted the BVH.
+//
+// Tried and dropped (B200, 4K teapot frame, bounce kernel 2.3 ms): postponing leaves into a per-lane queue so
+// that node visits and triangle tests run in separate, fuller phases — 15-25% slower (more box and triangle
+// tests because t_best tightens later, plus the queue bookkeeping), see DESIGN.md "What did not work".
 template <bool STATS>
-__global__ void __launch_bounds__(WF_BLOCK, 4)
-k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __restrict__ qd,
-           const uint32_t* __restrict__ n_ptr, uint32_t n_const, float2* __restrict__ hit_out,
-           uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max, uint32_t refill_min,
-           TraceCounters* __restrict__ counters) {
-    const uint32_t n = n_ptr ? *n_ptr : n_const;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    uint32_t chunk_next = 0, chunk_end = 0;       // warp-uniform
-    bool exhausted = (n == 0u);
-
-    bool active = false;
-    uint32_t ray_id = 0;
-    TravState s;
-    s.sp = 0; s.cur = 0; s.tbest = FLT_MAX; s.h.t = FLT_MAX; s.h.slot = -1; s.h.orig = 0xffffffffu;
-    // Traversal stack in SHARED memory, one 4-byte code per entry, laid out [depth][thread] so a warp never
-    // bank-conflicts.  As thread-local arrays (first version) the stacks went through L1, took ~40% of it and
-    // pushed the BVH nodes out: L1 hit rate 81%, 53-59% of stall samples on long_scoreboard for bounce rays.
-    extern __shared__ uint32_t smem_stack[];
-    uint32_t* const stack = smem_stack + threadIdx.x;     // entry k lives at stack[k * WF_BLOCK]
-    unsigned long long n_node = 0, n_tri = 0;
-
-    // root description (uniform)
-    const float4 r0 = __ldg(sc.nodes + 0), r1 = __ldg(sc.nodes + 1);
-    uint32_t root_code;
-    if (sc.n_prims == 0u) root_code = LEAF_FLAG;                                     // leaf with 0 primitives
-    else if (brute) root_code = 0xfffffffeu;                                        // handled separately
-    else if (__float_as_uint(r1.w) != 0u) root_code = LEAF_FLAG | (__float_as_uint(r0.w) << 3) | __float_as_uint(r1.w);
-    else root_code = __float_as_uint(r0.w);
-
-    auto finish = [&]() {
-        __stcs(hit_out + ray_id, make_float2(s.h.t, __int_as_float(s.h.slot)));
-        active = false;
-    };
-    // next work item from the stack (skipping entries the current bound already rules out) or finish the ray
+__device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, bool& trav, uint32_t* stack,
+                                           uint32_t k_nodes, unsigned long long& n_node,
+                                           unsigned long long& n_tri) {
     auto pop = [&]() {
-        if (s.sp == 0) { finish(); return; }
+        if (s.sp == 0) { trav = false; return; }
         --s.sp;
         s.cur = stack[s.sp * WF_BLOCK];
     };
-
-    for (;;) {
-        // ---- refill idle lanes from the queue ----
-        const unsigned need = __ballot_sync(FULL, !active);
-        if (!exhausted && ((uint32_t)__popc(need) >= refill_min)) {
-            if (chunk_next >= chunk_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(work_counter, WF_CHUNK);
-                base = __shfl_sync(FULL, base, 0);
-                if (base >= n) { exhausted = true; }
-                else { chunk_next = base; chunk_end = min(base + WF_CHUNK, n); }
-            }
-            if (!exhausted) {
-                const uint32_t idx = chunk_next + __popc(need & lt_mask);
-                if (!active && idx < chunk_end) {
-                    const float4 ro = __ldcs(qo + idx);      // streamed once: keep it out of L1
-                    if (__float_as_uint(ro.w) != INVALID_SLOT) {
-                        const float4 rd = __ldcs(qd + idx);
-                        ray_id = idx;
-                        s.o = mk(ro.x, ro.y, ro.z);
-                        s.d = mk(rd.x, rd.y, rd.z);
-                        s.ix = fminf(fmaxf(1.0f / s.d.x, -1e30f), 1e30f);
-                        s.iy = fminf(fmaxf(1.0f / s.d.y, -1e30f), 1e30f);
-                        s.iz = fminf(fmaxf(1.0f / s.d.z, -1e30f), 1e30f);
-                        s.ox = -s.o.x * s.ix; s.oy = -s.o.y * s.iy; s.oz = -s.o.z * s.iz;
-                        s.tbest = FLT_MAX;
-                        s.h.t = FLT_MAX; s.h.slot = -1; s.h.orig = 0xffffffffu;
-                        s.sp = 0;
-                        s.cur = root_code;
-                        active = true;
-                    }
-                }
-                chunk_next = min(chunk_next + (uint32_t)__popc(need), chunk_end);
-            }
-        }
-        if (__ballot_sync(FULL, active) == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-
-        if (brute) {   // validation mode: linear scan, no BVH
-            if (active) {
-                for (uint32_t k = 0; k < sc.n_prims; ++k) {
-                    float t;
-                    if (STATS) ++n_tri;
-                    const float4* q = sc.tri + (size_t)RTB_TRI_F4 * k;
-                    if (tri_test(q, s.o, s.d, s.h.slot >= 0, s.h.t, &t)) {
-                        const uint32_t orig = __float_as_uint(__ldg(q + 1).w);
-                        if (s.h.slot < 0 || t < s.h.t || (t == s.h.t && orig < s.h.orig)) { s.h.t = t; s.h.slot = (int)k; s.h.orig = orig; }
-                    }
-                }
-                finish();
-            }
-            continue;
-        }
-
-        // ---- traversal rounds until enough lanes are idle again ----
-        for (;;) {
-            // phase 1: at most `descend_max` internal-node steps per round.  Unbounded descent (classic
-            // while-while) left lanes that reached a leaf waiting for the slowest lane of the warp: 9-16 of 32
-            // lanes active on bounce rays (ncu, profiles/r1_v2_*).
 #pragma unroll 1
-            for (uint32_t it = 0; it < descend_max; ++it) {
-                const bool go = active && !(s.cur & LEAF_FLAG);
-                if (!__any_sync(FULL, go)) break;
-                if (!go) continue;
-                const float4* np = sc.nodes + 2u * s.cur;
-                const float4 a0 = __ldg(np + 0), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
-                if (STATS) n_node += 2;
-                float ta, tb;
-                bool hit_a, hit_b;
-                {
-                    const float x0 = fmaf(a0.x, s.ix, s.ox), x1 = fmaf(a1.x, s.ix, s.ox);
-                    const float y0 = fmaf(a0.y, s.iy, s.oy), y1 = fmaf(a1.y, s.iy, s.oy);
-                    const float z0 = fmaf(a0.z, s.iz, s.oz), z1 = fmaf(a1.z, s.iz, s.oz);
-                    ta = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-                    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.0000005f;
-                    hit_a = (ta <= tf) && (ta <= s.tbest);
-                }
-                {
-                    const float x0 = fmaf(b0.x, s.ix, s.ox), x1 = fmaf(b1.x, s.ix, s.ox);
-                    const float y0 = fmaf(b0.y, s.iy, s.oy), y1 = fmaf(b1.y, s.iy, s.oy);
-                    const float z0 = fmaf(b0.z, s.iz, s.oz), z1 = fmaf(b1.z, s.iz, s.oz);
-                    tb = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-                    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.0000005f;
-                    hit_b = (tb <= tf) && (tb <= s.tbest);
-                }
-                // child code: internal -> its left-child index; leaf -> LEAF_FLAG | first<<3 | count
-                const uint32_t ca_cnt = __float_as_uint(a1.w), cb_cnt = __float_as_uint(b1.w);
-                const uint32_t ca = ca_cnt ? (LEAF_FLAG | (__float_as_uint(a0.w) << 3) | ca_cnt) : __float_as_uint(a0.w);
-                const uint32_t cb = cb_cnt ? (LEAF_FLAG | (__float_as_uint(b0.w) << 3) | cb_cnt) : __float_as_uint(b0.w);
-                if (hit_a && hit_b) {
-                    const bool a_first = ta <= tb;
-                    stack[s.sp * WF_BLOCK] = a_first ? cb : ca;
-                    ++s.sp;
-                    s.cur = a_first ? ca : cb;
-                } else if (hit_a) {
-                    s.cur = ca;
-                } else if (hit_b) {
-                    s.cur = cb;
-                } else {
-                    pop();
-                }
-            }
-            // phase 2: the leaf this lane holds (if it reached one)
-            if (active && (s.cur & LEAF_FLAG)) {
-                const uint32_t first = (s.cur & ~LEAF_FLAG) >> 3, cnt = s.cur & 7u;
-                for (uint32_t k = first; k < first + cnt; ++k) {
-                    float t;
-                    if (STATS) ++n_tri;
-                    const float4* q = sc.tri + (size_t)RTB_TRI_F4 * k;
-                    if (tri_test(q, s.o, s.d, s.h.slot >= 0, s.h.t, &t)) {
-                        const uint32_t orig = __float_as_uint(__ldg(q + 1).w);
-                        if (s.h.slot < 0 || t < s.h.t || (t == s.h.t && orig < s.h.orig)) {
-                            s.h.t = t; s.h.slot = (int)k; s.h.orig = orig;
-                            if (t < s.tbest) s.tbest = t;      // a NaN t never tightens the bound
-                        }
-                    }
-                }
-                pop();
-            }
-            const unsigned act = __ballot_sync(FULL, active);
-            if (act == 0u) break;
-            if (!exhausted && (32u - __popc(act)) >= refill_min) break;
+    for (uint32_t it = 0; it < k_nodes; ++it) {
+        const bool go = trav && !(s.cur & LEAF_FLAG);
+        if (!__any_sync(FULL, go)) break;
+        if (!go) continue;
+        // one BVH4 node = one 128-byte line: 4 child boxes (SoA) + 4 child codes
+        const float4* np = sc.nodes4 + 8u * s.cur;
+        const float4 lx = __ldg(np + 0), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3);
+        const float4 lz = __ldg(np + 4), hz = __ldg(np + 5);
+        const uint4 cd = __ldg(reinterpret_cast<const uint4*>(np + 6));
+        if (STATS) n_node += 4;
+        const float INF = __int_as_float(0x7f800000);
+        float key[4];
+        uint32_t code[4] = {cd.x, cd.y, cd.z, cd.w};
+#define RTB_SLAB(c, LX, HX, LY, HY, LZ, HZ)                                                             \
+        {                                                                                               \
+            const float x0 = fmaf(LX, s.ix, s.ox), x1 = fmaf(HX, s.ix, s.ox);                           \
+            const float y0 = fmaf(LY, s.iy, s.oy), y1 = fmaf(HY, s.iy, s.oy);                           \
+            const float z0 = fmaf(LZ, s.iz, s.oz), z1 = fmaf(HZ, s.iz, s.oz);                           \
+            const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));    \
+            const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.0000005f;    \
+            key[c] = ((tn <= tf) && (tn <= s.tbest) && code[c] != 0u) ? tn : INF;                       \
+        }
+        RTB_SLAB(0, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x)
+        RTB_SLAB(1, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y)
+        RTB_SLAB(2, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z)
+        RTB_SLAB(3, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w)
+#undef RTB_SLAB
+        // sort the (up to 4) hits near-to-far: 5 compare-exchanges
+#define RTB_CE(a, b)                                                                  \
+        {                                                                             \
+            const bool sw = key[a] > key[b];                                          \
+            const float ka = sw ? key[b] : key[a], kb = sw ? key[a] : key[b];         \
+            const uint32_t ca_ = sw ? code[b] : code[a], cb_ = sw ? code[a] : code[b]; \
+            key[a] = ka; key[b] = kb; code[a] = ca_; code[b] = cb_;                   \
+        }
+        RTB_CE(0, 1) RTB_CE(2, 3) RTB_CE(0, 2) RTB_CE(1, 3) RTB_CE(1, 2)
+#undef RTB_CE
+        if (key[0] == INF) {
+            pop();
+        } else {
+            s.cur = code[0];                                   // nearest first, the rest far-to-near on the stack
+            if (key[3] < INF) { stack[s.sp * WF_BLOCK] = code[3]; ++s.sp; }
+            if (key[2] < INF) { stack[s.sp * WF_BLOCK] = code[2]; ++s.sp; }
+            if (key[1] < INF) { stack[s.sp * WF_BLOCK] = code[1]; ++s.sp; }
         }
     }
+    if (trav && (s.cur & LEAF_FLAG)) {
+        const uint32_t first = (s.cur & ~LEAF_FLAG) >> 3, cnt = s.cur & 7u;
+        for (uint32_t k = first; k < first + cnt; ++k) {
+            float t;
+            if (STATS) ++n_tri;
+            const float4* q = sc.tri + (size_t)RTB_TRI_F4 * k;
+            if (tri_test(q, s.o, s.d, s.h.slot >= 0, s.h.t, &t)) {
+                const uint32_t orig = __float_as_uint(__ldg(q + 1).w);
+                if (s.h.slot < 0 || t < s.h.t || (t == s.h.t && orig < s.h.orig)) {
+                    s.h.t = t; s.h.slot = (int)k; s.h.orig = orig;
+                    if (t < s.tbest) s.tbest = t;      // a NaN t never tightens the bound
+                }
+            }
+        }
+        pop();
+    }
+}
 
+// validation mode (RTB_FLAG_BRUTE): linear scan over every primitive, no BVH
+template <bool STATS>
+__device__ __forceinline__ void brute_scan(const SceneDev& sc, TravState& s, unsigned long long& n_tri) {
+    for (uint32_t k = 0; k < sc.n_prims; ++k) {
+        float t;
+        if (STATS) ++n_tri;
+        const float4* q = sc.tri + (size_t)RTB_TRI_F4 * k;
+        if (tri_test(q, s.o, s.d, s.h.slot >= 0, s.h.t, &t)) {
+            const uint32_t orig = __float_as_uint(__ldg(q + 1).w);
+            if (s.h.slot < 0 || t < s.h.t || (t == s.h.t && orig < s.h.orig)) { s.h.t = t; s.h.slot = (int)k; s.h.orig = orig; }
+        }
+    }
+}
+
+// Warp-level work fetch: lanes in `need` get consecutive queue indices; one global atomic per WF_CHUNK rays.
+struct WorkFetch {
+    uint32_t chunk_next = 0, chunk_end = 0;   // warp-uniform
+    bool exhausted = false;
+    // returns this lane's queue index or 0xffffffff
+    __device__ __forceinline__ uint32_t fetch(unsigned need, bool me, uint32_t n, uint32_t* counter, unsigned lane) {
+        if (exhausted || need == 0u) return 0xffffffffu;
+        if (chunk_next >= chunk_end) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(counter, WF_CHUNK);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n) { exhausted = true; return 0xffffffffu; }
+            chunk_next = base; chunk_end = min(base + WF_CHUNK, n);
+        }
+        const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
+        chunk_next = min(chunk_next + (uint32_t)__popc(need), chunk_end);
+        return (me && idx < chunk_end) ? idx : 0xffffffffu;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// stage 1: closest hit of the primary rays, persistent threads with per-lane refill
+// ---------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK, 4)
+k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __restrict__ qd, uint32_t n,
+           float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max,
+           uint32_t refill_min, TraceCounters* __restrict__ counters) {
+    extern __shared__ uint32_t smem_stack[];
+    uint32_t* const stack = smem_stack + threadIdx.x;     // entry k lives at stack[k * WF_BLOCK]
+    const unsigned lane = threadIdx.x & 31u;
+    WorkFetch wf;
+    wf.exhausted = (n == 0u);
+    const uint32_t root_code = root_code_of(sc);
+    bool trav = false;
+    uint32_t ray_id = 0;
+    TravState s;
+    start_ray(s, mk(0.f, 0.f, 0.f), mk(1.f, 1.f, 1.f), root_code);
+    unsigned long long n_node = 0, n_tri = 0;
+
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !trav);
+        if (!wf.exhausted && (uint32_t)__popc(need) >= refill_min) {
+            const uint32_t idx = wf.fetch(need, !trav, n, work_counter, lane);
+            if (idx != 0xffffffffu) {
+                const float4 ro = __ldcs(qo + idx);      // streamed once: keep it out of L1
+                if (__float_as_uint(ro.w) != INVALID_SLOT) {
+                    const float4 rd = __ldcs(qd + idx);
+                    ray_id = idx;
+                    start_ray(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), root_code);
+                    trav = true;
+                }
+            }
+        }
+        if (__ballot_sync(FULL, trav) == 0u) {
+            if (wf.exhausted) break;
+            continue;
+        }
+        for (;;) {
+            const bool was = trav;
+            if (brute) { if (trav) { brute_scan<STATS>(sc, s, n_tri); trav = false; } }
+            else trav_round<STATS>(sc, s, trav, stack, descend_max, n_node, n_tri);
+            if (was && !trav) __stcs(hit_out + ray_id, make_float2(s.h.t, __int_as_float(s.h.slot)));
+            const unsigned act = __ballot_sync(FULL, trav);
+            if (act == 0u) break;
+            if (!wf.exhausted && (32u - __popc(act)) >= refill_min) break;
+        }
+    }
     if (STATS) {
         for (int off = 16; off > 0; off >>= 1) {
             n_node += __shfl_xor_sync(FULL, n_node, off);
@@ -270,21 +291,45 @@ k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __res
 }
 
 // ---------------------------------------------------------------------------
-// stage 2: shade one queue level
+// path bookkeeping shared by the shade kernel and the bounce kernel
 // ---------------------------------------------------------------------------
-struct ShadeArgs {
-    const float4* qo_in; const float4* qd_in; const float2* hit;
-    const uint32_t* n_in_ptr; uint32_t n_in_const;
-    float4* qo_out; float4* qd_out; uint32_t* n_out;
-    float4* stack;            // [maxdepth][n_slots]
+struct PathBuffers {
+    float4* stack;            // [maxdepth][n_slots]  (colour, alpha) per bounce level
     uint64_t* rng_state;      // [n_slots]
-    float4* acc;              // [n_slots] (multi-sample only)
+    float4* acc;              // [n_slots] running sample sum (multi-sample only)
     float4* rgba; uint32_t* prim_out; float* t_out;
-    uint32_t n_slots, level, smp;
+    uint32_t n_slots;
 };
 
-__global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const ViewDev vw, const ShadeArgs a) {
-    const uint32_t n = a.n_in_ptr ? *a.n_in_ptr : a.n_in_const;
+// A path of `levels` bounces ended with colour `term`: unwind the recursion innermost-first (mix_color :299-301),
+// then add the sample to the pixel and, on the last sample, scale and store it (walk_ray_set :1422-1426).
+__device__ __forceinline__ void finish_path(const ViewDev& vw, const PathBuffers& pb, uint32_t slot, uint32_t smp,
+                                            uint32_t levels, V3 term) {
+    V3 c = term;
+    for (int k = (int)levels - 1; k >= 0; --k) {
+        const float4 e = pb.stack[(size_t)k * pb.n_slots + slot];
+        c = mix_color(mk(e.x, e.y, e.z), c, e.w);
+    }
+    V3 sum = mk(0.f, 0.f, 0.f);
+    if (smp != vw.s_begin) { const float4 p = pb.acc[slot]; sum = mk(p.x, p.y, p.z); }
+    sum = vadd(sum, c);
+    if (smp + 1u == vw.s_end) {
+        if (!(vw.flags & RTB_FLAG_SUM_ONLY)) sum = vmul(sum, __fdiv_rn(1.0f, (float)vw.spp));
+        const Pixel px = slot_to_pixel(vw, slot);
+        __stcs(pb.rgba + px.out_idx, make_float4(sum.x, sum.y, sum.z, 0.f));
+    } else {
+        pb.acc[slot] = make_float4(sum.x, sum.y, sum.z, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage 2: shade the primary hits, emit the bounce queue
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const ViewDev vw, const PathBuffers pb,
+                                                  const float4* __restrict__ qo_in, const float4* __restrict__ qd_in,
+                                                  const float2* __restrict__ hit, uint32_t n, uint32_t smp,
+                                                  float4* __restrict__ qo_out, float4* __restrict__ qd_out,
+                                                  uint32_t* __restrict__ n_out) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n_round = (n + 31u) & ~31u;
@@ -292,86 +337,151 @@ __global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const ViewD
         bool emit = false;
         V3 no = mk(0.f, 0.f, 0.f), nd = mk(0.f, 0.f, 0.f);
         uint32_t slot = INVALID_SLOT;
-        if (i < n) {
-            const float4 ro = a.qo_in[i];
-            slot = __float_as_uint(ro.w);
-        }
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) { ro = __ldcs(qo_in + i); slot = __float_as_uint(ro.w); }
         if (slot != INVALID_SLOT) {
-            const float4 ro = a.qo_in[i], rd = a.qd_in[i];
+            const float4 rd = __ldcs(qd_in + i);
             const V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
-            const float2 hr = a.hit[i];
+            const float2 hr = __ldcs(hit + i);
             const int prim_slot = __float_as_int(hr.y);
             const float t = hr.x;
-            V3 term;
-            uint32_t levels = a.level;     // entries on this path's mix stack
-            if (a.level == 0u && a.smp == 0u && (a.prim_out || a.t_out)) {
+            V3 term = mk(0.f, 0.f, 0.f);
+            uint32_t levels = 0;
+            if (smp == 0u && (pb.prim_out || pb.t_out)) {
                 const Pixel px = slot_to_pixel(vw, slot);
-                if (a.prim_out) a.prim_out[px.out_idx] = prim_slot >= 0 ? __float_as_uint(__ldg(sc.tri + (size_t)RTB_TRI_F4 * prim_slot + 1).w) : 0u;
-                if (a.t_out) a.t_out[px.out_idx] = prim_slot >= 0 ? t : 0.0f;
+                if (pb.prim_out) pb.prim_out[px.out_idx] = prim_slot >= 0 ? __float_as_uint(__ldg(sc.tri + (size_t)RTB_TRI_F4 * prim_slot + 1).w) : 0u;
+                if (pb.t_out) pb.t_out[px.out_idx] = prim_slot >= 0 ? t : 0.0f;
             }
             if (prim_slot < 0) {
                 term = sky_color();                                            // project_ray miss :1284
             } else {
                 Rng g;
-                g.state = a.rng_state[slot];
+                g.state = pb.rng_state[slot];
                 V3 color;
                 float alpha = 0.f;
                 if (shade_hit(sc, prim_slot, t, o, d, g, &color, &alpha, &no, &nd) == 0) {
                     term = color;
                 } else {
-                    a.stack[(size_t)a.level * a.n_slots + slot] = make_float4(color.x, color.y, color.z, alpha);
-                    levels = a.level + 1u;
-                    if (a.level + 1u < vw.maxdepth) { emit = true; a.rng_state[slot] = g.state; }
-                    else term = mk(0.f, 0.f, 0.f);                             // project_ray(depth 0): black :1261
+                    pb.stack[slot] = make_float4(color.x, color.y, color.z, alpha);   // level 0
+                    levels = 1u;
+                    if (1u < vw.maxdepth) { emit = true; pb.rng_state[slot] = g.state; }
+                    // else: project_ray(depth 0) returns black (:1261), term stays black
                 }
             }
-            if (!emit) {
-                // unwind the recursion innermost-first, then add the sample to the pixel (:1422-1426)
-                V3 c = term;
-                for (int k = (int)levels - 1; k >= 0; --k) {
-                    const float4 e = a.stack[(size_t)k * a.n_slots + slot];
-                    c = mix_color(mk(e.x, e.y, e.z), c, e.w);
-                }
-                V3 sum = mk(0.f, 0.f, 0.f);
-                if (a.smp != vw.s_begin) { const float4 p = a.acc[slot]; sum = mk(p.x, p.y, p.z); }
-                sum = vadd(sum, c);
-                if (a.smp + 1u == vw.s_end) {
-                    if (!(vw.flags & RTB_FLAG_SUM_ONLY)) sum = vmul(sum, __fdiv_rn(1.0f, (float)vw.spp));
-                    const Pixel px = slot_to_pixel(vw, slot);
-                    a.rgba[px.out_idx] = make_float4(sum.x, sum.y, sum.z, 0.f);
-                } else {
-                    a.acc[slot] = make_float4(sum.x, sum.y, sum.z, 0.f);
-                }
-            }
+            if (!emit) finish_path(vw, pb, slot, smp, levels, term);
         }
-        // stream compaction of the surviving paths into the next queue
+        // stream compaction of the surviving paths into the bounce queue
         const unsigned m = __ballot_sync(FULL, emit);
         if (m) {
             uint32_t base = 0;
             const int leader = __ffs(m) - 1;
-            if ((int)lane == leader) base = atomicAdd(a.n_out, (uint32_t)__popc(m));
+            if ((int)lane == leader) base = atomicAdd(n_out, (uint32_t)__popc(m));
             base = __shfl_sync(FULL, base, leader);
             if (emit) {
                 const uint32_t j = base + __popc(m & ((1u << lane) - 1u));
-                a.qo_out[j] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-                a.qd_out[j] = make_float4(nd.x, nd.y, nd.z, 0.f);
+                qo_out[j] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
+                qd_out[j] = make_float4(nd.x, nd.y, nd.z, 0.f);
             }
         }
     }
 }
 
-// per-sample roll-up: total bounce rays += sum n[1..], then reset the per-level counters
-struct WfCounters {
-    uint32_t n[RTB_MAX_DEPTH + 1];
-    uint32_t work[RTB_MAX_DEPTH + 1];
-};
-__global__ void k_wf_tally(WfCounters* c, TraceCounters* totals) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long s = 0;
-        for (int k = 1; k <= RTB_MAX_DEPTH; ++k) s += c->n[k];
-        atomicAdd(&totals->rays, s);   // several lanes (streams) of one GPU share the totals
-        for (int k = 0; k <= RTB_MAX_DEPTH; ++k) { c->n[k] = 0u; c->work[k] = 0u; }
+// ---------------------------------------------------------------------------
+// stage 3: every bounce path to its end, persistent
+// ---------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK, WF_BOUNCE_MIN_BLOCKS)
+k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const float4* __restrict__ qo,
+            const float4* __restrict__ qd, const uint32_t* __restrict__ n_ptr, uint32_t smp,
+            uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max, uint32_t refill_min,
+            TraceCounters* __restrict__ counters) {
+    extern __shared__ uint32_t smem_stack[];
+    uint32_t* const stack = smem_stack + threadIdx.x;
+    const uint32_t n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31u;
+    WorkFetch wf;
+    wf.exhausted = (n == 0u);
+    const uint32_t root_code = root_code_of(sc);
+
+    bool has_path = false;   // this lane carries a path (pixel) ...
+    bool trav = false;       // ... whose current ray is still being traversed
+    uint32_t slot = 0, level = 0;
+    Rng g; g.state = 0;
+    TravState s;
+    start_ray(s, mk(0.f, 0.f, 0.f), mk(1.f, 1.f, 1.f), root_code);
+    unsigned long long n_node = 0, n_tri = 0, n_rays = 0;
+
+    for (;;) {
+        // ---- service: shade finished rays (bounce again in place or end the path), then refill dead lanes ----
+        const unsigned waiting = __ballot_sync(FULL, !trav);
+        if ((uint32_t)__popc(waiting) >= refill_min || __ballot_sync(FULL, trav) == 0u) {
+            if (has_path && !trav) {
+                // project_ray :1283-1293 for the ray that just finished; `level` entries are on the mix stack
+                V3 term = mk(0.f, 0.f, 0.f);
+                bool ended = true;
+                if (s.h.slot < 0) {
+                    term = sky_color();
+                } else {
+                    V3 color, no, nd;
+                    float alpha = 0.f;
+                    if (shade_hit(sc, s.h.slot, s.h.t, s.o, s.d, g, &color, &alpha, &no, &nd) == 0) {
+                        term = color;
+                    } else {
+                        pb.stack[(size_t)level * pb.n_slots + slot] = make_float4(color.x, color.y, color.z, alpha);
+                        ++level;
+                        if (level < vw.maxdepth) {          // project_ray(depth-1) with depth-1 > 0
+                            start_ray(s, no, nd, root_code);
+                            trav = true; ended = false; ++n_rays;
+                        }                                   // else depth 0: black (:1261), not counted
+                    }
+                }
+                if (ended) { finish_path(vw, pb, slot, smp, level, term); has_path = false; }
+            }
+            const unsigned need = __ballot_sync(FULL, !has_path);
+            const uint32_t idx = wf.fetch(need, !has_path, n, work_counter, lane);
+            if (idx != 0xffffffffu) {
+                const float4 ro = __ldcs(qo + idx), rd = __ldcs(qd + idx);
+                slot = __float_as_uint(ro.w);
+                level = 1u;
+                g.state = pb.rng_state[slot];
+                start_ray(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), root_code);
+                has_path = true; trav = true; ++n_rays;
+            }
+        }
+        if (__ballot_sync(FULL, has_path) == 0u) {
+            if (wf.exhausted) break;
+            continue;
+        }
+        // ---- traversal rounds until enough lanes wait for service ----
+        for (;;) {
+            if (brute) { if (trav) { brute_scan<STATS>(sc, s, n_tri); trav = false; } }
+            else trav_round<STATS>(sc, s, trav, stack, descend_max, n_node, n_tri);
+            const unsigned act = __ballot_sync(FULL, trav);
+            if (act == 0u || (32u - __popc(act)) >= refill_min) break;
+        }
     }
+    for (int off = 16; off > 0; off >>= 1) {
+        n_rays += __shfl_xor_sync(FULL, n_rays, off);
+        if (STATS) {
+            n_node += __shfl_xor_sync(FULL, n_node, off);
+            n_tri += __shfl_xor_sync(FULL, n_tri, off);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&counters->rays, n_rays);
+        if (STATS) { atomicAdd(&counters->node_tests, n_node); atomicAdd(&counters->tri_tests, n_tri); }
+    }
+}
+
+// per-sample reset of the queue / work counters
+struct WfCounters {
+    uint32_t n_bounce;        // size of the bounce queue
+    uint32_t work_primary;    // work-fetch counters of the two persistent kernels
+    uint32_t work_bounce;
+    uint32_t pad;
+};
+__global__ void k_wf_tally(WfCounters* c) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { c->n_bounce = 0u; c->work_primary = 0u; c->work_bounce = 0u; }
 }
 
 }  // namespace
@@ -381,12 +491,12 @@ __global__ void k_wf_tally(WfCounters* c, TraceCounters* totals) {
 // ---------------------------------------------------------------------------
 size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample) {
     size_t b = 0;
-    b += 4 * sizeof(float4) * (size_t)n_slots;                  // two ray queues (o, d)
-    b += sizeof(float2) * (size_t)n_slots;                      // hit records
-    b += sizeof(float4) * (size_t)n_slots * maxdepth;           // mix stacks
-    b += sizeof(uint64_t) * (size_t)n_slots;                    // RNG
-    if (multisample) b += sizeof(float4) * (size_t)n_slots;     // sample sums
-    b += 256 + sizeof(WfCounters);
+    b += 4 * (sizeof(float4) * (size_t)n_slots + 256);          // primary + bounce ray queues (o, d)
+    b += sizeof(float2) * (size_t)n_slots + 256;                // hit records of the primary rays
+    b += sizeof(float4) * (size_t)n_slots * maxdepth + 256;     // mix stacks
+    b += sizeof(uint64_t) * (size_t)n_slots + 256;              // RNG
+    if (multisample) b += sizeof(float4) * (size_t)n_slots + 256;   // sample sums
+    b += 512;
     return b;
 }
 
@@ -399,28 +509,36 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     // carve the workspace
     char* p = (char*)workspace;
     auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
-    float4* qo[2]; float4* qd[2];
-    qo[0] = (float4*)take(sizeof(float4) * n_slots); qd[0] = (float4*)take(sizeof(float4) * n_slots);
-    qo[1] = (float4*)take(sizeof(float4) * n_slots); qd[1] = (float4*)take(sizeof(float4) * n_slots);
+    float4* qo0 = (float4*)take(sizeof(float4) * n_slots); float4* qd0 = (float4*)take(sizeof(float4) * n_slots);
+    float4* qo1 = (float4*)take(sizeof(float4) * n_slots); float4* qd1 = (float4*)take(sizeof(float4) * n_slots);
     float2* hit = (float2*)take(sizeof(float2) * n_slots);
-    float4* stack = (float4*)take(sizeof(float4) * (size_t)n_slots * vw.maxdepth);
-    uint64_t* rng = (uint64_t*)take(sizeof(uint64_t) * n_slots);
-    float4* acc = multi ? (float4*)take(sizeof(float4) * n_slots) : nullptr;
+    PathBuffers pb;
+    pb.stack = (float4*)take(sizeof(float4) * (size_t)n_slots * vw.maxdepth);
+    pb.rng_state = (uint64_t*)take(sizeof(uint64_t) * n_slots);
+    pb.acc = multi ? (float4*)take(sizeof(float4) * n_slots) : nullptr;
+    pb.rgba = d_rgba; pb.prim_out = d_prim; pb.t_out = d_t; pb.n_slots = n_slots;
     WfCounters* wc = (WfCounters*)take(sizeof(WfCounters));
 
-    // persistent grid: as many CTAs as fit, given the shared-memory traversal stacks ((height+2) x 4 B per thread)
+    // persistent grids: as many CTAs as fit, given the shared-memory traversal stacks (3 entries per BVH4 level, 4 B each, per thread)
     const bool stats = (vw.flags & RTB_FLAG_STATS) != 0;
-    const size_t smem = (size_t)(sc.height + 2u) * WF_BLOCK * sizeof(uint32_t);
-    int dev = 0, sms = 0, per_sm = 0;
+    const size_t smem = (size_t)sc.stack4 * WF_BLOCK * sizeof(uint32_t);
+    int dev = 0, sms = 0, per_sm_t = 0, per_sm_b = 0;
     RTB_CUDA(cudaGetDevice(&dev));
     RTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (smem > 48 * 1024) {
         RTB_CUDA(cudaFuncSetAttribute(k_wf_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RTB_CUDA(cudaFuncSetAttribute(k_wf_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTB_CUDA(cudaFuncSetAttribute(k_wf_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTB_CUDA(cudaFuncSetAttribute(k_wf_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (stats) RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace<true>, WF_BLOCK, smem));
-    else RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace<false>, WF_BLOCK, smem));
-    const int tb = sms * (per_sm > 0 ? per_sm : 1);
+    if (stats) {
+        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_wf_trace<true>, WF_BLOCK, smem));
+        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_wf_bounce<true>, WF_BLOCK, smem));
+    } else {
+        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_wf_trace<false>, WF_BLOCK, smem));
+        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_wf_bounce<false>, WF_BLOCK, smem));
+    }
+    const int grid_t = sms * std::max(per_sm_t, 1), grid_b = sms * std::max(per_sm_b, 1);
     const uint32_t shade_blocks = std::min<uint32_t>((n_slots + 255u) / 256u, 148u * 16u);
     const uint32_t brute = (vw.flags & RTB_FLAG_BRUTE) ? 1u : 0u;
     static uint32_t descend_max = 0, refill_min = 0;
@@ -433,25 +551,24 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
 
     RTB_CUDA(cudaMemsetAsync(wc, 0, sizeof(WfCounters), stream));
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
-        k_wf_raygen<<<(n_slots + 255u) / 256u, 256, 0, stream>>>(vw, smp, n_slots, qo[0], qd[0], rng);
-        if (launches) ++*launches;
-        for (uint32_t level = 0; level < vw.maxdepth; ++level) {
-            const int in = level & 1u, out = in ^ 1;
-            const uint32_t* n_ptr = level ? &wc->n[level] : nullptr;
+        k_wf_raygen<<<(n_slots + 255u) / 256u, 256, 0, stream>>>(vw, smp, n_slots, qo0, qd0, pb.rng_state);
+        if (stats)
+            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, d_counters);
+        else
+            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, d_counters);
+        k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, qo0, qd0, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
+        if (launches) *launches += 3;
+        if (vw.maxdepth > 1) {
             if (stats)
-                k_wf_trace<true><<<tb, WF_BLOCK, smem, stream>>>(sc, qo[in], qd[in], n_ptr, n_slots, hit, &wc->work[level], brute, descend_max, refill_min, d_counters);
+                k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, d_counters);
             else
-                k_wf_trace<false><<<tb, WF_BLOCK, smem, stream>>>(sc, qo[in], qd[in], n_ptr, n_slots, hit, &wc->work[level], brute, descend_max, refill_min, d_counters);
-            ShadeArgs a;
-            a.qo_in = qo[in]; a.qd_in = qd[in]; a.hit = hit; a.n_in_ptr = n_ptr; a.n_in_const = n_slots;
-            a.qo_out = qo[out]; a.qd_out = qd[out]; a.n_out = &wc->n[level + 1];
-            a.stack = stack; a.rng_state = rng; a.acc = acc; a.rgba = d_rgba; a.prim_out = d_prim; a.t_out = d_t;
-            a.n_slots = n_slots; a.level = level; a.smp = smp;
-            k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, a);
-            if (launches) *launches += 2;
+                k_wf_bounce<false><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, d_counters);
+            if (launches) ++*launches;
         }
-        k_wf_tally<<<1, 32, 0, stream>>>(wc, d_counters);
-        if (launches) ++*launches;
+        if (smp + 1 < vw.s_end) {
+            k_wf_tally<<<1, 32, 0, stream>>>(wc);
+            if (launches) ++*launches;
+        }
     }
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
