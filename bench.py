@@ -35,9 +35,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH, HEIGHT, MAXDEPTH, SPP, SEED = 3840, 2160, 5, 1, 7
-WORKLOAD = "teapot 4K multi-bounce (main.rs scene, 6721 tris, 3840x2160, maxdepth 5, 1 spp, shipped materials)"
+SEED = 7
 FP32_LANES_PER_SM, N_SM = 128, 148
+
+# name -> (description, width, height, maxdepth, spp, partition)
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (default)
+    "teapot4k": ("teapot 4K multi-bounce (main.rs scene, 6721 tris, 3840x2160, maxdepth 5, 1 spp, shipped materials)",
+                 3840, 2160, 5, 1, "bands"),
+    # configs[3]: ~1M triangles, GPU LBVH build + incoherent (mirror) bounces
+    "field1m": ("teapot field, 156 instanced teapots = 985,921 tris, Reflective{0}, 2560x1440, maxdepth 5, 1 spp",
+                2560, 1440, 5, 1, "bands"),
+    # configs[4]: progressive render, samples partitioned over the GPUs + reduce of the accumulation buffers
+    "progressive8k": ("8K progressive, main.rs scene, 7680x4320, maxdepth 5, 64 spp, samples partitioned over ranks + "
+                      "NCCL reduce(sum) of the f32 accumulation buffers + 1/spp", 7680, 4320, 5, 64, "samples"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_wf_bounce launch of the teapot4k frame at N=1, from the
+# `ncu --set full` capture summarised in profiles/ (see DESIGN.md "Roofline"); null for every other configuration.
+NCU_TRAFFIC_BOUNCE_TEAPOT4K = 390.3e6
 
 
 def measured_peaks():
@@ -101,21 +116,42 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU reference arm (the oracle restatement running the reference's octree algorithm)
 # --------------------------------------------------------------------------------------------
-def cpu_reference(rows, threads=None, repeat=1):
-    """Times the oracle in reference-algorithm mode (octree, row work-queue over host threads) on image
-    rows [rows[0], rows[1]) of the benchmark frame.  Returns (Mrays/s, rays, seconds, cores)."""
+def build_scene(R, name):
+    return R.teapot_field_scene() if name == "field1m" else R.main_scene(deterministic=False)
+
+
+def oracle_scene(O, scene, name, cores):
+    """Reference-algorithm mode (octree) wherever the reference's builder can handle the scene; the 1M-triangle
+    scene cannot be built as an octree in reasonable time, there the oracle uses its own BVH."""
+    accel = O.ACCEL_BVH if name == "field1m" else O.ACCEL_OCTREE
+    return O.Scene(scene.tris.view(O.TRI_DTYPE), accel, build_threads=cores), ("bvh" if accel == O.ACCEL_BVH else "octree")
+
+
+def cpu_reference(name, rows, threads=None, repeat=1):
+    """Times the oracle on image rows [rows[0], rows[1]) of the workload's frame (all samples).
+    Returns (Mrays/s, rays, seconds, cores, accel)."""
     from oracle import oracle as O
     import rust_raytrace_b200 as R   # host-side scene construction only (no GPU use)
+    desc, W, H, maxdepth, spp, _ = WORKLOADS[name]
     cores = threads or os.cpu_count() or 1
-    scene = R.main_scene(deterministic=False)
-    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE, build_threads=cores)   # build excluded, as main.rs:160 vs :191
-    ov = O.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
+    osc, accel = oracle_scene(O, build_scene(R, name), name, cores)   # build excluded, as main.rs:160 vs :191
+    ov = O.main_viewport(W, H, maxdepth, spp)
     best = None
     for _ in range(repeat):
         _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
         if best is None or st.seconds < best[2]:
-            best = (st.rays / st.seconds / 1e6, int(st.rays), float(st.seconds), cores)
+            best = (st.rays / st.seconds / 1e6, int(st.rays), float(st.seconds), cores, accel)
     return best
+
+
+def cpu_sample_rows(name):
+    """A bounded band through the middle of the frame (teapot + both disks), ~10-30 s of CPU work."""
+    desc, W, H, maxdepth, spp, _ = WORKLOADS[name]
+    if name == "teapot4k":
+        return (0, H)                 # the whole frame: 14.26 M rays, ~9 s on 16 host threads
+    if name == "field1m":
+        return (H // 2 + 100, H // 2 + 164)
+    return (H // 2, H // 2 + 4)       # 64 spp: 4 rows x 7680 px x 64 samples
 
 
 def run_reference(args):
@@ -124,15 +160,20 @@ def run_reference(args):
         return
     from oracle import oracle as O
     import rust_raytrace_b200 as R   # host-side scene construction only (no GPU use)
+    name = args.workload
+    desc, W, H, maxdepth, spp, _ = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    scene = R.main_scene(deterministic=False)
-    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE, build_threads=cores)
-    ov = O.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
-    # bounded sample per step: a band through the middle of the frame (teapot + both disks), sized so that
-    # warmup+steps stay within a few minutes whatever the host: 2 s of work at the rate of a 16-row probe
-    _, _, _, probe = osc.render(ov, seed=SEED, threads=cores, rows=(1072, 1088), want_ids=False)
-    n_rows = int(min(HEIGHT, max(16, 16 * 2.0 / max(probe.seconds, 1e-3)))) // 8 * 8
-    rows = (max(0, 1080 - n_rows // 2), min(HEIGHT, 1080 - n_rows // 2 + n_rows))
+    osc, accel = oracle_scene(O, build_scene(R, name), name, cores)
+    ov = O.main_viewport(W, H, maxdepth, spp)
+    # bounded sample per step, sized so that warmup+steps stay within a few minutes whatever the host:
+    # ~2 s of work at the rate of a small probe band through the middle of the frame
+    mid = cpu_sample_rows(name)[0]
+    probe_rows = 16 if spp == 1 else 1
+    _, _, _, probe = osc.render(ov, seed=SEED, threads=cores, rows=(mid, mid + probe_rows), want_ids=False)
+    n_rows = int(min(H - mid, max(probe_rows, probe_rows * 2.0 / max(probe.seconds, 1e-3))))
+    if spp == 1:
+        n_rows = max(8, n_rows // 8 * 8)
+    rows = (mid - n_rows // 2, mid - n_rows // 2 + n_rows) if spp == 1 else (mid, mid + n_rows)
     rates, secs, rays = [], [], 0
     for i in range(args.warmup + args.steps):
         _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
@@ -140,16 +181,14 @@ def run_reference(args):
         if i >= args.warmup:
             rates.append(st.rays / st.seconds / 1e6); secs.append(st.seconds)
     value = float(np.mean(rates))
-    frame_rays = 14259831
+    sample = (f"image rows {rows[0]}..{rows[1]} of {H} ({rays} rays per step), oracle in "
+              f"{'reference-algorithm mode (octree 204,894 nodes, row work-queue)' if accel == 'octree' else 'BVH mode (row work-queue)'}")
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3),
-        "ms_per_frame_extrapolated": frame_rays / (value * 1e6) * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"rows {rows[0]}..{rows[1]} of {HEIGHT} per step"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                         "sample": f"image rows {rows[0]}..{rows[1]} of the 4K frame, {rays} rays per step, "
-                                   "oracle in reference-algorithm mode (octree 204,894 nodes, row work-queue)"},
+        "config": {"workload": desc, "sample": f"rows {rows[0]}..{rows[1]} of {H} per step"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -174,40 +213,61 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import rust_raytrace_b200 as R
-    from rust_raytrace_b200 import _lib
+    from rust_raytrace_b200 import _lib, dist as RD
     L = _lib.lib()
 
+    name = args.workload
+    desc, W, H, maxdepth, spp, partition = WORKLOADS[name]
+    by_samples = partition == "samples"
     dev_ids = (C.c_int * 1)(local_rank)
     _lib.check(L.rtb_init(1, dev_ids), "rtb_init")
-    scene = R.main_scene(deterministic=False)
+    scene = build_scene(R, name)
     h = scene.upload()
     info = scene.info()
-    view = R.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
+    view = R.main_viewport(W, H, maxdepth, spp)
     view.seed = SEED
-    npix = WIDTH * HEIGHT
+    npix = W * H
+    if by_samples:
+        my_view = RD.sample_view(view, rank, world)           # samples [b, e) of spp, RTB_FLAG_SUM_ONLY
+        tile_rank, tile_world = 0, 1
+    else:
+        my_view = view
+        tile_rank, tile_world = rank, world
 
-    d_rgba = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda")
+    d_rgba = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     # an explicit (non-null) stream: handle 0 would mean "the library's own stream" to rtb_render_device,
     # and torch.cuda.Event only sees the stream it is recorded on
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    sp = C.c_void_p(stream.cuda_stream)
 
-    def step(stats=None):
-        _lib.check(L.rtb_render_device(h, C.byref(view), 0, rank, world, d_rgba.data_ptr(), None, None,
-                                       C.c_void_p(stream.cuda_stream), stats), "rtb_render_device")
+    def render(v, stats=None):
+        if v is not None:
+            _lib.check(L.rtb_render_device(h, C.byref(v), 0, tile_rank, tile_world, d_rgba.data_ptr(), None, None, sp,
+                                           stats), "rtb_render_device")
 
-    # one counted frame: rays and (with the STATS kernel variant) node / triangle tests per ray
+    def step():
+        render(my_view)
+        if by_samples:
+            if my_view is None:
+                d_rgba.zero_()
+            RD.reduce_samples(d_rgba, spp)                     # NCCL reduce(sum) to rank 0 + 1/spp (rtb_scale_device)
+
+    def with_flags(v, flags):
+        if v is None:
+            return None
+        c = _lib.RtbView.from_buffer_copy(v)
+        c.flags |= flags
+        return c
+
+    # one counted frame: rays, then (STATS kernel variant) node / triangle tests per ray, per kernel
     st = _lib.RtbStats()
-    step(C.byref(st))
+    render(my_view, C.byref(st))
     my_rays = int(st.rays)
-    vstat = _lib.RtbView.from_buffer_copy(view)
-    vstat.flags |= _lib.RTB_FLAG_STATS
     st2 = _lib.RtbStats()
-    _lib.check(L.rtb_render_device(h, C.byref(vstat), 0, rank, world, d_rgba.data_ptr(), None, None,
-                                   C.c_void_p(stream.cuda_stream), C.byref(st2)), "rtb_render_device(stats)")
-    n_node, n_tri = st2.node_tests / max(st2.rays, 1), st2.tri_tests / max(st2.rays, 1)
+    render(with_flags(my_view, _lib.RTB_FLAG_STATS), C.byref(st2))
 
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
@@ -230,9 +290,23 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop(local_rank) if rank == 0 else None
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     ms_mine = float(np.mean(ms_steps))
+
+    # per-stage device times of the same step, live (CUDA events on the launching stream between the kernels),
+    # still under the clock sampler; used for the roofline of the dominant kernel
+    stage_ms = np.zeros(4)
+    n_timing = 0
+    if my_view is not None:
+        stt = _lib.RtbStats()
+        tv = with_flags(my_view, _lib.RTB_FLAG_TIMING)
+        for _ in range(5):
+            flush.fill_(0)
+            render(tv, C.byref(stt))
+            stage_ms += np.array(stt.ms_stage[:])
+            n_timing += 1
+        stage_ms /= n_timing
+    clocks = sampler.stop(local_rank) if rank == 0 else None
 
     tens = torch.tensor([ms_mine, float(my_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -251,23 +325,26 @@ def run_gpu(args):
         ids = (C.c_int * args.gpus)(*range(args.gpus))
         scene.release()
         _lib.check(L.rtb_init(args.gpus, ids), "rtb_init(all)")
-        sc_all = R.main_scene(deterministic=False)
+        sc_all = build_scene(R, name)
         caster = R.B200RayCaster(seed=SEED)
         caster._n_gpus = args.gpus
-        host = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
+        host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
         data = host.numpy()
-        vv = R.main_viewport(WIDTH, HEIGHT, MAXDEPTH, SPP)
-        for _ in range(max(args.warmup, 3)):
-            caster.walk_rays(vv, sc_all, data, threads=args.gpus)
+        vv = R.main_viewport(W, H, maxdepth, spp)
+        call = (lambda: caster.walk_rays_progressive(vv, sc_all, data, threads=args.gpus)) if by_samples else \
+               (lambda: caster.walk_rays(vv, sc_all, data, threads=args.gpus))
+        e_steps = args.steps if not by_samples else max(1, min(args.steps, 3))
+        for _ in range(max(args.warmup, 3) if not by_samples else 1):
+            call()
         t0 = time.perf_counter()
         rays_e2e = 0
-        for _ in range(args.steps):
-            ctx = caster.walk_rays(vv, sc_all, data, threads=args.gpus)
-            rays_e2e += ctx.total_rays
+        for _ in range(e_steps):
+            rays_e2e += call().total_rays
         dt = time.perf_counter() - t0
-        e2e = {"value": rays_e2e / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / args.steps * 1e3,
+        e2e = {"value": rays_e2e / dt / 1e6, "unit": "Mrays/s", "ms_per_frame": dt / e_steps * 1e3,
                "h2d_bytes_per_step": C.sizeof(_lib.RtbView), "d2h_bytes_per_step": npix * 16,
-               "api": "B200RayCaster.walk_rays -> rtb_render (pinned host image, scene resident)"}
+               "api": ("B200RayCaster.walk_rays_progressive -> rtb_render_progressive" if by_samples else
+                       "B200RayCaster.walk_rays -> rtb_render") + " (pinned host image, scene resident)"}
         assert int(caster.stats.rays) == int(total_rays), (caster.stats.rays, total_rays)
         sc_all.release()
     if world > 1:
@@ -275,38 +352,54 @@ def run_gpu(args):
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = measured_peaks()
-        rays_per_launch = total_rays / world
-        b_ray = n_node * 32 + n_tri * 80 + 16                      # node 32 B, triangle 80 B, pixel 16 B
-        w_ray = n_node * 24 + n_tri * 54 + 45                      # FP32 lane-ops per ray
-        launch_s = ms_mine * 1e-3
-        ach_gbs = rays_per_launch * b_ray / launch_s / 1e9
+        # algorithmic bytes / FP32 lane-ops per ray = 32 B, 24 ops per AABB test; 80 B, 54 ops per exact
+        # triangle test; 16 B per output pixel, 45 ops per generated ray.  Dominant kernel = k_wf_bounce (rank 0's launch).
+        b_rays = max(int(st2.bounce_rays), 1)
+        nb_node, nb_tri = st2.node_tests_bounce / b_rays, st2.tri_tests_bounce / b_rays
+        n_node, n_tri = st2.node_tests / max(st2.rays, 1), st2.tri_tests / max(st2.rays, 1)
+        bounce_s = max(stage_ms[3], 1e-6) * 1e-3
+        bytes_launch = b_rays * (nb_node * 32 + nb_tri * 80 + 16)
+        ops_launch = b_rays * (nb_node * 24 + nb_tri * 54 + 45)
         fp32_peak = N_SM * FP32_LANES_PER_SM * sm_max_mhz * 1e6
-        ach_fp32 = rays_per_launch * w_ray / launch_s
+        ach_gbs = bytes_launch / bounce_s / 1e9
+        step_ops = my_rays * (n_node * 24 + n_tri * 54 + 45)
+        traffic = NCU_TRAFFIC_BOUNCE_TEAPOT4K if (name == "teapot4k" and world == 1) else None
         cpu = None
         if world == 1 and not args.no_cpu:
-            mr, rays, s, cores = cpu_reference((1000, 1128))
+            rows = cpu_sample_rows(name)
+            mr, rays, s, cores, accel = cpu_reference(name, rows)
             cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                   "sample": f"image rows 1000..1128 of the same 4K frame ({rays} rays, {s:.1f} s), oracle in "
-                             "reference-algorithm mode (octree, row work-queue, all host threads)"}
+                   "sample": f"image rows {rows[0]}..{rows[1]} of the same frame ({rays} rays, {s:.1f} s), oracle in "
+                             + ("reference-algorithm mode (octree, row work-queue, all host threads)" if accel == "octree"
+                                else "BVH mode (the reference octree cannot be built for 1M triangles), all host threads")}
+        launches_per_step = int(st.kernel_launches) + (1 if by_samples else 0)
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_frame": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_frame": int(total_rays), "partition": f"8-row bands, band b -> rank b % {world}",
-                       "l2": "flushed between timed iterations (256 MiB fill); scene (1.3 MB) is re-read from HBM each step",
+            "config": {"workload": desc, "rays_per_frame": int(total_rays),
+                       "partition": (f"samples: rank r renders samples [64r/{world}, 64(r+1)/{world}) of the full frame, then reduce"
+                                     if by_samples else f"8-row bands, band b -> rank b % {world}"),
+                       "l2": "flushed between timed iterations (256 MiB fill); the scene is re-read from HBM each step",
                        "bvh": {"nodes": info.n_nodes, "leaves": info.n_leaves, "max_leaf": info.max_leaf,
                                "height": info.tree_height, "ms_build": info.ms_build, "ms_upload": info.ms_upload},
                        "node_tests_per_ray": n_node, "tri_tests_per_ray": n_tri, "wall_s_timed_region": t_wall},
-            "gpu_launches": args.steps * 1 * world,
+            "gpu_launches": args.steps * launches_per_step * world,
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "algorithmic bytes = rays * (32*N_node + 80*N_tri + 16); the working set is L1/L2 resident, "
-                                 "so this path is bounded by FP32 issue + cache latency, see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32_issue", "achieved": ach_fp32 / 1e12, "peak": fp32_peak / 1e12,
-                              "unit": "Tlane-op/s", "frac": ach_fp32 / fp32_peak,
-                              "lane_ops_per_ray": w_ray, "kernel": "k_trace"},
+            "stages_ms": {k: float(v) for k, v in zip(_lib.RTB_STAGES, stage_ms)},
+            "roofline": {"bound": "hbm", "kernel": "k_wf_bounce", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "launch_ms": float(stage_ms[3]), "share_of_step": float(stage_ms[3] / max(stage_ms.sum(), 1e-9)),
+                         "algorithmic_bytes_per_launch": bytes_launch,
+                         "per_ray": {"aabb_tests": nb_node, "tri_tests": nb_tri, "rays": b_rays},
+                         "note": "algorithmic bytes = rays*(32*N_aabb + 80*N_tri + 16) are served by L1/L2 (the scene is "
+                                 "cache resident; measured DRAM traffic is `traffic`), so `frac` can exceed 1 and the "
+                                 "kernel's real bound is FP32/ALU issue under divergence: see roofline_fp32"},
+            "roofline_fp32": {"bound": "fp32_issue", "kernel": "k_wf_bounce", "achieved": ops_launch / bounce_s / 1e12,
+                              "peak": fp32_peak / 1e12, "unit": "Tlane-op/s", "frac": ops_launch / bounce_s / fp32_peak,
+                              "whole_step_frac": step_ops / (ms_mine * 1e-3) / fp32_peak,
+                              "lane_ops_per_ray": nb_node * 24 + nb_tri * 54 + 45},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -320,6 +413,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="teapot4k", choices=sorted(WORKLOADS),
+                    help="teapot4k = the configuration BASELINE.json's metric is quoted on (default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

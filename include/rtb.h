@@ -89,9 +89,14 @@ enum {
     RTB_FLAG_STATS    = 2u,   /* also count node/triangle tests (slower kernel variant)            */
     RTB_FLAG_BRUTE    = 4u,   /* validation: ignore the BVH, test every primitive (the GPU analogue of
                                  build_trivial_bounding_box, raytrace.rs:847-856)                  */
-    RTB_FLAG_MEGAKERNEL = 8u  /* A/B: the one-kernel-per-frame renderer (rtb_trace.cu) instead of the
+    RTB_FLAG_MEGAKERNEL = 8u, /* A/B: the one-kernel-per-frame renderer (rtb_trace.cu) instead of the
                                  default wavefront pipeline (rtb_wavefront.cu); same results        */
+    RTB_FLAG_TIMING   = 16u   /* rtb_render_device only: bracket every pipeline stage with CUDA events on the
+                                 launching stream and report RtbStats.ms_stage (one piece, one lane)  */
 };
+
+/* Pipeline stages of the wavefront renderer, indices into RtbStats.ms_stage. */
+enum { RTB_STAGE_RAYGEN = 0, RTB_STAGE_TRACE = 1, RTB_STAGE_SHADE = 2, RTB_STAGE_BOUNCE = 3, RTB_N_STAGES = 4 };
 
 typedef struct RtbStats {
     uint64_t rays;            /* project_ray calls with depth>0 — the reference's "Rays" (raytrace.rs:1278) */
@@ -101,6 +106,10 @@ typedef struct RtbStats {
     double   ms_total;        /* host wall time of the call incl. copies */
     uint32_t kernel_launches; /* kernels launched by this call */
     uint32_t n_gpus;
+    uint64_t bounce_rays;        /* rays traced by the bounce kernel (rays - primary rays)                */
+    uint64_t node_tests_bounce;  /* the share of node_tests / tri_tests spent in the bounce kernel        */
+    uint64_t tri_tests_bounce;   /*   (RTB_FLAG_STATS only)                                               */
+    double   ms_stage[4];        /* RTB_FLAG_TIMING: device ms per stage, summed over samples (CUDA events) */
 } RtbStats;
 
 typedef struct RtbSceneInfo {
@@ -161,6 +170,12 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
  * per-GPU f32 sum buffers combined over NVLink peer memory: every GPU reduces and normalises one
  * horizontal band reading its peers' buffers directly, then copies the band to rgba_out.  */
 int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, RtbStats* stats);
+
+/* One-process-per-GPU sample partition (torchrun): every rank renders its samples [sample_begin, sample_end) with
+ * RTB_FLAG_SUM_ONLY through rtb_render_device, the sum buffers are combined by an NCCL reduce (the caller's
+ * torch.distributed / ncclReduce), and the root applies walk_ray_set's final `* (1/spp)` (raytrace.rs:1426) with this
+ * call: d_rgba[i].xyz *= 1/spp, lane 3 = 0, on GPU slot `gpu` and stream `stream` (NULL = the library's stream). */
+int rtb_scale_device(float* d_rgba, uint64_t npix, uint32_t spp, int gpu, void* stream);
 
 /* (c*255.) as u8 quantiser of write_png (raytrace.rs:1468-1473) on the GPU: rgba f32 host -> rgb8 host. */
 int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out);

@@ -126,6 +126,9 @@ def lib():
     L.or_render.argtypes = [vp, C.POINTER(OrView), C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp,
                             C.POINTER(OrStats)]
     L.or_render.restype = C.c_int
+    L.or_render_samples.argtypes = [vp, C.POINTER(OrView), C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_int, vp, vp, vp, C.POINTER(OrStats)]
+    L.or_render_samples.restype = C.c_int
     L.or_quantize_rgb8.argtypes = [vp, C.c_uint64, vp]
     L.or_selftest_face_collision.restype = C.c_int
     L.or_rng_f32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
@@ -257,6 +260,16 @@ class Scene:
         t = C.c_float()
         idx = lib().or_scene_closest_hit(self.h, _f3(orig), _f3(dir3), C.byref(t))
         return idx, t.value
+
+    def render_samples(self, v: OrView, s0, s1, seed=0, threads=None, sum_only=True):
+        """Samples [s0, s1) of v.spp only; with sum_only the un-normalised sum (multi-GPU sample partition checker)."""
+        threads = threads or os.cpu_count() or 1
+        H, W = v.height, v.width
+        rgba = np.zeros((H, W, 4), np.float32)
+        st = OrStats()
+        lib().or_render_samples(self.h, C.byref(v), seed, threads, 0, H, int(s0), int(s1), 1 if sum_only else 0,
+                                rgba.ctypes.data, None, None, C.byref(st))
+        return rgba, st
 
     def render(self, v: OrView, seed=0, threads=None, rows=None, want_ids=True):
         """DefaultRayCaster.walk_rays equivalent -> (rgba[H,W,4], prim[H,W], t[H,W], OrStats)."""

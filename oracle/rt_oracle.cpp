@@ -988,6 +988,14 @@ uint32_t or_scene_closest_hit(const OrScene* s, const float orig[3], const float
 
 int or_render(const OrScene* s, const OrView* vc, uint64_t seed, int threads, uint32_t row0, uint32_t row1,
               float* rgba, uint32_t* prim, float* tbuf, OrStats* stats) {
+    return or_render_samples(s, vc, seed, threads, row0, row1, 0, vc->spp, 0, rgba, prim, tbuf, stats);
+}
+
+/* The sample loop of rs:1418-1426 restricted to samples [s0, s1) of v.spp (the jitter rule still looks at v.spp);
+ * sum_only = 1 skips the final `* (1/spp)` so that partial sums of different sample ranges can be added up. */
+int or_render_samples(const OrScene* s, const OrView* vc, uint64_t seed, int threads, uint32_t row0, uint32_t row1,
+                      uint32_t s0, uint32_t s1, int sum_only,
+                      float* rgba, uint32_t* prim, float* tbuf, OrStats* stats) {
     View v = view_from_c(*vc);
     if (row1 > v.height) row1 = v.height;
     if (threads < 1) threads = 1;
@@ -1002,7 +1010,7 @@ int or_render(const OrScene* s, const OrView* vc, uint64_t seed, int threads, ui
             for (uint32_t col = 0; col < v.width; col++) {                                     /* rs:1413-1427 */
                 V3 acc = mk(0, 0, 0);
                 uint64_t pix = (uint64_t)row * v.width + col;
-                for (uint32_t smp = 0; smp < v.spp; smp++) {
+                for (uint32_t smp = s0; smp < s1; smp++) {
                     Rng g; g.seed(seed, pix, smp);
                     Ray ray = pixel_ray(v, row, col, &g);
                     uint32_t pr = 0; float tt = 0;
@@ -1010,7 +1018,7 @@ int or_render(const OrScene* s, const OrView* vc, uint64_t seed, int threads, ui
                     acc = vadd(acc, col3);
                     if (smp == 0) { if (prim) prim[pix] = pr; if (tbuf) tbuf[pix] = tt; }
                 }
-                V3 o = vmul(acc, 1.0f / (float)v.spp);
+                V3 o = sum_only ? acc : vmul(acc, 1.0f / (float)v.spp);
                 rgba[4 * pix + 0] = o.x; rgba[4 * pix + 1] = o.y; rgba[4 * pix + 2] = o.z; rgba[4 * pix + 3] = 0.0f;
             }
         }

@@ -129,6 +129,11 @@ uint32_t or_scene_closest_hit(const OrScene* s, const float orig[3], const float
 int  or_render(const OrScene* s, const OrView* v, uint64_t seed, int threads,
                uint32_t row0, uint32_t row1,
                float* rgba, uint32_t* prim, float* t, OrStats* stats);
+/* Same, for samples [s0, s1) of v->spp only; sum_only != 0 returns the un-normalised sample sum (the checker for
+ * the sample-partitioned multi-GPU mode, where partial sums are reduced before the 1/spp scale). */
+int  or_render_samples(const OrScene* s, const OrView* v, uint64_t seed, int threads,
+                       uint32_t row0, uint32_t row1, uint32_t s0, uint32_t s1, int sum_only,
+                       float* rgba, uint32_t* prim, float* t, OrStats* stats);
 /* write_png quantiser :1468-1473: (c*255.) as u8, rgb only. */
 void or_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb);
 

@@ -5,13 +5,13 @@ scene preparation in C++) and `raytrace.py`, the host-side mirror of the referen
 """
 from . import _lib  # noqa: F401
 from .raytrace import (B200RayCaster, ProgressCtx, Scene, SurfaceKind, Viewport, create_transform, create_viewport,  # noqa: F401
-                       main_scene, main_viewport, make_color, make_disk, make_dummy_triangle, make_sphere,
+                       main_scene, main_viewport, teapot_field_scene, make_color, make_disk, make_dummy_triangle, make_sphere,
                        make_triangle, make_vec, new_image, obj_parser, populate_triangle_numbers, quantize_rgb8,
                        to_radians, unit, write_ppm)
 
 __all__ = [
     "B200RayCaster", "ProgressCtx", "Scene", "SurfaceKind", "Viewport", "create_transform", "create_viewport",
-    "main_scene", "main_viewport", "make_color", "make_disk", "make_dummy_triangle", "make_sphere", "make_triangle",
+    "main_scene", "main_viewport", "teapot_field_scene", "make_color", "make_disk", "make_dummy_triangle", "make_sphere", "make_triangle",
     "make_vec", "new_image", "obj_parser", "populate_triangle_numbers", "quantize_rgb8", "to_radians", "unit",
     "write_ppm",
 ]

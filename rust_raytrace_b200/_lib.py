@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("RTB_LIB", os.path.join(_PKG, "librtb.so"))   # RTB_LI
 
 RTB_OK, RTB_ERR_NO_DEVICE, RTB_ERR_CUDA, RTB_ERR_INVALID, RTB_ERR_NOMEM = 0, -1, -2, -3, -4
 RTB_SOLID, RTB_MATTE, RTB_REFLECTIVE = 0, 1, 2
-RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL = 1, 2, 4, 8
+RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL, RTB_FLAG_TIMING = 1, 2, 4, 8, 16
+RTB_STAGES = ("raygen", "trace", "shade", "bounce")
 RTB_MAX_DEPTH = 16
 
 # numpy mirror of RtbTriangle (35 x 4 bytes; reference field order raytrace.rs:326-337)
@@ -65,6 +66,10 @@ class RtbStats(C.Structure):
         ("ms_total", C.c_double),
         ("kernel_launches", C.c_uint32),
         ("n_gpus", C.c_uint32),
+        ("bounce_rays", C.c_uint64),
+        ("node_tests_bounce", C.c_uint64),
+        ("tri_tests_bounce", C.c_uint64),
+        ("ms_stage", C.c_double * 4),
     ]
 
 
@@ -93,7 +98,7 @@ class RtbSurface(C.Structure):
 RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render", "rtb_render_device", "rtb_render_progressive",
-    "rtb_quantize_rgb8", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
+    "rtb_quantize_rgb8", "rtb_scale_device", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
 ]
 RTBH_SYMBOLS = [
     "rtbh_make_color", "rtbh_unit", "rtbh_to_radians", "rtbh_make_triangle", "rtbh_make_dummy_triangle",
@@ -137,6 +142,7 @@ def lib():
     L.rtb_render_device.argtypes = [vp, C.POINTER(RtbView), C.c_int, u32, u32, vp, vp, vp, vp, C.POINTER(RtbStats)]
     L.rtb_render_progressive.argtypes = [vp, C.POINTER(RtbView), vp, C.POINTER(RtbStats)]
     L.rtb_quantize_rgb8.argtypes = [vp, C.c_uint64, vp]
+    L.rtb_scale_device.argtypes = [vp, C.c_uint64, u32, C.c_int, vp]
     L.rtb_partition_rows.argtypes = [u32, u32, u32, vp, u32]
     L.rtb_host_register.argtypes = [vp, C.c_size_t]
     L.rtb_host_unregister.argtypes = [vp]

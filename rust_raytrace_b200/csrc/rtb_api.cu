@@ -53,6 +53,7 @@ void free_gpu_scene(GpuScene& g) {
     for (auto& l : g.lanes) {
         cudaFree(l.d_ws);
         if (l.done) cudaEventDestroy(l.done);
+        for (auto& e : l.stage_ev) if (e) cudaEventDestroy(e);
         if (l.st) cudaStreamDestroy(l.st);
     }
     if (g.fork_ev) cudaEventDestroy(g.fork_ev);
@@ -141,7 +142,13 @@ int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd
         lane.ws_bytes = need + need / 16;
     }
     *primary_rays += owned_pixels(vd) * (uint64_t)(vd.s_end - vd.s_begin);
-    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, lane.d_ws, d_rgba, d_prim, d_t, g.d_counters, st, launches);
+    cudaEvent_t* sev = nullptr;
+    if (vd.flags & RTB_FLAG_TIMING) {
+        for (auto& e : lane.stage_ev) if (!e) RTB_CUDA(cudaEventCreate(&e));
+        sev = lane.stage_ev;
+    }
+    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, lane.d_ws, d_rgba, d_prim, d_t, g.d_counters, st, launches,
+                                sev, lane.stage_ms);
 }
 
 int env_int(const char* name, int dflt) {
@@ -365,8 +372,14 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
     }
     uint64_t primary = 0;
     const size_t px = (size_t)vd.my_tile_rows * RTB_TILE_H * vd.width;
-    const uint32_t pieces = (uint32_t)env_int("RTB_PIECES", (int)std::min<size_t>(RTB_DEFAULT_PIECES_DEVICE, std::max<size_t>(1, px / (1u << 20))));
-    const uint32_t n_lanes = (uint32_t)env_int("RTB_LANES", RTB_DEFAULT_LANES);
+    uint32_t pieces = (uint32_t)env_int("RTB_PIECES", (int)std::min<size_t>(RTB_DEFAULT_PIECES_DEVICE, std::max<size_t>(1, px / (1u << 20))));
+    uint32_t n_lanes = (uint32_t)env_int("RTB_LANES", RTB_DEFAULT_LANES);
+    const bool timing = (view->flags & RTB_FLAG_TIMING) != 0;
+    if (timing) {
+        if (!stats) return fail(RTB_ERR_INVALID, "RTB_FLAG_TIMING needs a stats pointer");
+        pieces = 1; n_lanes = 1;
+        for (float& m : g.lanes[0].stage_ms) m = 0.f;
+    }
     rc = render_pieces(g, s->info.n_prims, vd, (float4*)d_rgba, d_prim, d_t, st, pieces, n_lanes, &launches, &primary,
                        [](uint32_t, const ViewDev&, cudaStream_t) { return (int)RTB_OK; });
     if (rc != RTB_OK) return rc;
@@ -379,6 +392,8 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
         RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
         std::memset(stats, 0, sizeof *stats);
         stats->rays = c.rays + primary; stats->node_tests = c.node_tests; stats->tri_tests = c.tri_tests;
+        stats->bounce_rays = c.rays; stats->node_tests_bounce = c.node_tests_bounce; stats->tri_tests_bounce = c.tri_tests_bounce;
+        if (timing) for (int k = 0; k < RTB_N_STAGES; ++k) stats->ms_stage[k] = g.lanes[0].stage_ms[k];
         stats->ms_render = ms; stats->ms_total = now_ms() - t0; stats->kernel_launches = launches; stats->n_gpus = 1;
     }
     return RTB_OK;
@@ -488,6 +503,7 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
         float ms = 0.f;
         RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
         st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
+        st.bounce_rays += c.rays; st.node_tests_bounce += c.node_tests_bounce; st.tri_tests_bounce += c.tri_tests_bounce;
         st.ms_render = std::max(st.ms_render, (double)ms);
     }
     st.rays += primary_total;
@@ -569,6 +585,7 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
         float ms = 0.f;
         RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
         st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
+        st.bounce_rays += c.rays; st.node_tests_bounce += c.node_tests_bounce; st.tri_tests_bounce += c.tri_tests_bounce;
         st.ms_render = std::max(st.ms_render, (double)ms);
     }
     st.rays += primary_total;
@@ -577,6 +594,15 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
     st.n_gpus = world;
     if (stats) *stats = st;
     return RTB_OK;
+}
+
+int rtb_scale_device(float* d_rgba, uint64_t npix, uint32_t spp, int gpu, void* stream) {
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    if (!d_rgba || spp == 0) return fail(RTB_ERR_INVALID, "rtb_scale_device: NULL buffer or spp == 0");
+    if (gpu < 0 || gpu >= (int)g_devices.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
+    RTB_CUDA(cudaSetDevice(g_devices[gpu]));
+    return rtb_launch_scale((float4*)d_rgba, npix, 1.0f / (float)spp, (cudaStream_t)stream);
 }
 
 int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out) {

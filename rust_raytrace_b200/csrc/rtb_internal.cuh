@@ -74,6 +74,8 @@ struct TraceCounters {
     unsigned long long rays;
     unsigned long long node_tests;
     unsigned long long tri_tests;
+    unsigned long long node_tests_bounce;   // share of the two above spent in k_wf_bounce
+    unsigned long long tri_tests_bounce;
 };
 
 // One compute lane of a GPU: a stream with its own wavefront workspace (ray queues, hit records, mix stacks, RNG).
@@ -82,6 +84,8 @@ struct GpuLane {
     cudaEvent_t done = nullptr;
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
+    cudaEvent_t stage_ev[RTB_N_STAGES + 1] = {};   // RTB_FLAG_TIMING: stage boundaries of one sample
+    float stage_ms[RTB_N_STAGES] = {};
 };
 
 // Per-GPU state of a scene.
@@ -149,10 +153,14 @@ int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint
 // The default renderer: raygen / persistent trace / shade+compact stages per bounce level.
 // counters->rays receives the BOUNCE rays only; the caller adds the primary rays (valid pixels x samples).
 size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample);
+// stage_ev (nullable): 5 events recorded at the stage boundaries of every sample; stage_ms accumulates their gaps
+// (this synchronises the stream once per sample: timing mode only).
 int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace, float4* d_rgba, uint32_t* d_prim,
-                         float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches);
+                         float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches,
+                         cudaEvent_t* stage_ev = nullptr, float* stage_ms = nullptr);
 
 int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream);
+int rtb_launch_scale(float4* d_rgba, uint64_t npix, float inv_spp, cudaStream_t stream);
 // Fused cross-GPU reduce of per-GPU sample sums over peer memory: out[i] = (sum_g bufs[g][i]) * inv_spp for
 // pixels [first, first+count).
 int rtb_launch_peer_reduce(const float4* const* d_bufs_on_device, int n_bufs, float inv_spp, uint64_t first,

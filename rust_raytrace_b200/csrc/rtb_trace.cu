@@ -256,6 +256,21 @@ int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint
     return RTB_OK;
 }
 
+// `data[col] = acc * (1/spp)` of walk_ray_set (raytrace.rs:1426) for a sample sum that was reduced across ranks
+__global__ void k_scale(float4* __restrict__ rgba, uint64_t npix, float inv_spp) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 c = rgba[i];
+        rgba[i] = make_float4(__fmul_rn(c.x, inv_spp), __fmul_rn(c.y, inv_spp), __fmul_rn(c.z, inv_spp), 0.f);
+    }
+}
+
+int rtb_launch_scale(float4* d_rgba, uint64_t npix, float inv_spp, cudaStream_t stream) {
+    if (npix == 0) return RTB_OK;
+    k_scale<<<148 * 8, 256, 0, stream>>>(d_rgba, npix, inv_spp);
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
+}
+
 int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream) {
     if (npix == 0) return RTB_OK;
     k_quantize<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(d_rgba, npix, d_rgb);

@@ -33,6 +33,8 @@ constexpr uint32_t INVALID_SLOT = 0xffffffffu;
 constexpr uint32_t LEAF_FLAG = 0x80000000u;
 constexpr uint32_t WF_CHUNK = 128;      // rays reserved per warp per global atomic
 constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent kernels
+constexpr int WF_OVF = 3 * (RTB_STACK / 2 + 1) + 2;   // worst-case BVH4 stack (tree height < RTB_STACK), thread-local overflow part
+constexpr int WF_SMEM_STACK = 8;        // stack entries per thread kept in shared memory
 #ifndef WF_BOUNCE_MIN_BLOCKS
 #define WF_BOUNCE_MIN_BLOCKS 8          // 64 registers: 32 warps/SM instead of 24 at the natural 80
 #endif
@@ -127,12 +129,20 @@ __device__ __forceinline__ void start_ray(TravState& s, V3 o, V3 d, uint32_t roo
 // tests because t_best tightens later, plus the queue bookkeeping), see DESIGN.md "What did not work".
 template <bool STATS>
 __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, bool& trav, uint32_t* stack,
-                                           uint32_t k_nodes, unsigned long long& n_node,
+                                           uint32_t* ovf, int smem_depth, uint32_t k_nodes, unsigned long long& n_node,
                                            unsigned long long& n_tri) {
+    // The first `smem_depth` stack entries live in shared memory, deeper ones (rare) in thread-local memory:
+    // sizing the shared stack for the worst case (3 entries per BVH4 level, 37 for the teapot scene) took 143 KB
+    // of each SM's 256 KB and grows with the tree height (a 1 M-triangle scene would drop to 4 CTAs/SM).  Measured on
+    // B200, 4K teapot frame: 40 entries 3.22 ms, 16: 3.21, 12: 3.20, 8: 3.18, 6: 3.15, 4: 3.16 — L1 capacity is not the limiter.
     auto pop = [&]() {
         if (s.sp == 0) { trav = false; return; }
         --s.sp;
-        s.cur = stack[s.sp * WF_BLOCK];
+        s.cur = s.sp < smem_depth ? stack[s.sp * WF_BLOCK] : ovf[s.sp - smem_depth];
+    };
+    auto push = [&](uint32_t code) {
+        if (s.sp < smem_depth) stack[s.sp * WF_BLOCK] = code; else ovf[s.sp - smem_depth] = code;
+        ++s.sp;
     };
 #pragma unroll 1
     for (uint32_t it = 0; it < k_nodes; ++it) {
@@ -176,9 +186,9 @@ __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, boo
             pop();
         } else {
             s.cur = code[0];                                   // nearest first, the rest far-to-near on the stack
-            if (key[3] < INF) { stack[s.sp * WF_BLOCK] = code[3]; ++s.sp; }
-            if (key[2] < INF) { stack[s.sp * WF_BLOCK] = code[2]; ++s.sp; }
-            if (key[1] < INF) { stack[s.sp * WF_BLOCK] = code[1]; ++s.sp; }
+            if (key[3] < INF) push(code[3]);
+            if (key[2] < INF) push(code[2]);
+            if (key[1] < INF) push(code[1]);
         }
     }
     if (trav && (s.cur & LEAF_FLAG)) {
@@ -240,9 +250,10 @@ template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK, 4)
 k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __restrict__ qd, uint32_t n,
            float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max,
-           uint32_t refill_min, TraceCounters* __restrict__ counters) {
+           uint32_t refill_min, int smem_depth, TraceCounters* __restrict__ counters) {
     extern __shared__ uint32_t smem_stack[];
     uint32_t* const stack = smem_stack + threadIdx.x;     // entry k lives at stack[k * WF_BLOCK]
+    uint32_t ovf[WF_OVF];
     const unsigned lane = threadIdx.x & 31u;
     WorkFetch wf;
     wf.exhausted = (n == 0u);
@@ -274,7 +285,7 @@ k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __res
         for (;;) {
             const bool was = trav;
             if (brute) { if (trav) { brute_scan<STATS>(sc, s, n_tri); trav = false; } }
-            else trav_round<STATS>(sc, s, trav, stack, descend_max, n_node, n_tri);
+            else trav_round<STATS>(sc, s, trav, stack, ovf, smem_depth, descend_max, n_node, n_tri);
             if (was && !trav) __stcs(hit_out + ray_id, make_float2(s.h.t, __int_as_float(s.h.slot)));
             const unsigned act = __ballot_sync(FULL, trav);
             if (act == 0u) break;
@@ -394,9 +405,10 @@ __global__ void __launch_bounds__(WF_BLOCK, WF_BOUNCE_MIN_BLOCKS)
 k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const float4* __restrict__ qo,
             const float4* __restrict__ qd, const uint32_t* __restrict__ n_ptr, uint32_t smp,
             uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max, uint32_t refill_min,
-            TraceCounters* __restrict__ counters) {
+            int smem_depth, TraceCounters* __restrict__ counters) {
     extern __shared__ uint32_t smem_stack[];
     uint32_t* const stack = smem_stack + threadIdx.x;
+    uint32_t ovf[WF_OVF];
     const uint32_t n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     WorkFetch wf;
@@ -455,7 +467,7 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
         // ---- traversal rounds until enough lanes wait for service ----
         for (;;) {
             if (brute) { if (trav) { brute_scan<STATS>(sc, s, n_tri); trav = false; } }
-            else trav_round<STATS>(sc, s, trav, stack, descend_max, n_node, n_tri);
+            else trav_round<STATS>(sc, s, trav, stack, ovf, smem_depth, descend_max, n_node, n_tri);
             const unsigned act = __ballot_sync(FULL, trav);
             if (act == 0u || (32u - __popc(act)) >= refill_min) break;
         }
@@ -469,7 +481,10 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
     }
     if (lane == 0) {
         atomicAdd(&counters->rays, n_rays);
-        if (STATS) { atomicAdd(&counters->node_tests, n_node); atomicAdd(&counters->tri_tests, n_tri); }
+        if (STATS) {
+            atomicAdd(&counters->node_tests, n_node); atomicAdd(&counters->tri_tests, n_tri);
+            atomicAdd(&counters->node_tests_bounce, n_node); atomicAdd(&counters->tri_tests_bounce, n_tri);
+        }
     }
 }
 
@@ -501,7 +516,8 @@ size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisam
 }
 
 int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace, float4* d_rgba, uint32_t* d_prim,
-                         float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches) {
+                         float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches,
+                         cudaEvent_t* stage_ev, float* stage_ms) {
     const uint32_t tiles_x8 = (vw.width + 7u) / 8u;
     const uint32_t n_slots = vw.my_tile_rows * 2u * tiles_x8 * 32u;
     if (n_slots == 0) return RTB_OK;
@@ -521,7 +537,10 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
 
     // persistent grids: as many CTAs as fit, given the shared-memory traversal stacks (3 entries per BVH4 level, 4 B each, per thread)
     const bool stats = (vw.flags & RTB_FLAG_STATS) != 0;
-    const size_t smem = (size_t)sc.stack4 * WF_BLOCK * sizeof(uint32_t);
+    static int smem_stack_cfg = -1;
+    if (smem_stack_cfg < 0) { const char* e = getenv("RTB_WF_STACK"); smem_stack_cfg = e ? std::max(1, atoi(e)) : WF_SMEM_STACK; }
+    const int smem_depth = std::min<int>((int)sc.stack4, smem_stack_cfg);
+    const size_t smem = (size_t)smem_depth * WF_BLOCK * sizeof(uint32_t);
     int dev = 0, sms = 0, per_sm_t = 0, per_sm_b = 0;
     RTB_CUDA(cudaGetDevice(&dev));
     RTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -550,20 +569,34 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     }
 
     RTB_CUDA(cudaMemsetAsync(wc, 0, sizeof(WfCounters), stream));
+    auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], stream); };
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
+        mark(0);
         k_wf_raygen<<<(n_slots + 255u) / 256u, 256, 0, stream>>>(vw, smp, n_slots, qo0, qd0, pb.rng_state);
+        mark(1);
         if (stats)
-            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, d_counters);
+            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, smem_depth, d_counters);
         else
-            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, d_counters);
+            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, smem_depth, d_counters);
+        mark(2);
         k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, qo0, qd0, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
+        mark(3);
         if (launches) *launches += 3;
         if (vw.maxdepth > 1) {
             if (stats)
-                k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, d_counters);
+                k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, smem_depth, d_counters);
             else
-                k_wf_bounce<false><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, d_counters);
+                k_wf_bounce<false><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, smem_depth, d_counters);
             if (launches) ++*launches;
+        }
+        mark(4);
+        if (stage_ev) {
+            RTB_CUDA(cudaEventSynchronize(stage_ev[4]));
+            for (int k = 0; k < RTB_N_STAGES; ++k) {
+                float ms = 0.f;
+                RTB_CUDA(cudaEventElapsedTime(&ms, stage_ev[k], stage_ev[k + 1]));
+                stage_ms[k] += ms;
+            }
         }
         if (smp + 1 < vw.s_end) {
             k_wf_tally<<<1, 32, 0, stream>>>(wc);

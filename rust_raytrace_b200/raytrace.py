@@ -388,6 +388,26 @@ def main_scene(deterministic=False, mesh_path=TEAPOT_MESH) -> Scene:
     return Scene(tris, boxes=((0.0, 0.0, 20.1), 20.0))
 
 
+def teapot_field_scene(nz=12, ny=13, seed=1, surface=None, scale=0.3, mesh_path=TEAPOT_MESH) -> Scene:
+    """BASELINE config 4: nz x ny instanced teapots (12 x 13 = 156 -> 985,920 triangles + the dummy) standing on a
+    grid that recedes from main.rs's camera, every instance with its own roll angle from an LCG (fixed seed) and
+    mirror-like `Reflective{scattering: 0}` surfaces so that bounce rays are incoherent.  All instances lie inside
+    main.rs's octree root cube ((0,0,20.1), 20), so the reference's visibility cull keeps every triangle."""
+    if surface is None:
+        surface = SurfaceKind.Reflective(0.0, make_color((252, 119, 0)), 0.5)
+    verts, faces = obj_parser.load_mesh_bin(mesh_path)
+    parts = [make_dummy_triangle()]
+    state = int(seed) & 0xFFFFFFFF
+    for iz in range(nz):
+        for iy in range(ny):
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF          # Numerical Recipes LCG
+            roll = 270.0 + 360.0 * (state >> 8) / float(1 << 24)
+            tf = create_transform(unit([0.0, 0.3, 1.0]), to_radians(roll))
+            off = [-1.2, (iy - (ny - 1) / 2.0) * 2.2, 3.0 + 2.0 * iz]
+            parts.append(obj_parser.mesh_to_triangles(verts, faces, off, scale, tf, surface, 0.05))
+    return Scene(np.concatenate(parts), boxes=((0.0, 0.0, 20.1), 20.0))
+
+
 def main_viewport(width, height, maxdepth=5, spp=1) -> RtbView:
     """main.rs:166-173 with aspect = height/width as in main.rs:96-110."""
     aspect = np.float32(height) / np.float32(width)

@@ -71,6 +71,10 @@ pub struct RtbStats {
     pub ms_total: f64,
     pub kernel_launches: u32,
     pub n_gpus: u32,
+    pub bounce_rays: u64,
+    pub node_tests_bounce: u64,
+    pub tri_tests_bounce: u64,
+    pub ms_stage: [f64; 4],
 }
 
 #[repr(C)]

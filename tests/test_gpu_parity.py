@@ -212,6 +212,20 @@ def test_sphere_scene_config1(R, O):
                      "spheres")
 
 
+def test_teapot_field_1m_triangles(R, O):
+    """BASELINE config 4: 156 instanced teapots = 985,920 triangles, mirror surfaces (incoherent bounces), GPU LBVH
+    build + traversal against the oracle's own BVH (the reference octree cannot be built at this size)."""
+    s = R.teapot_field_scene()
+    inf = s.info()
+    assert inf.n_tris == 985921 and inf.n_prims == 985920 and inf.max_leaf <= 4
+    _, order = s.download_bvh()
+    assert np.array_equal(np.sort(order), np.arange(1, 985921, dtype=np.uint32))
+    osc = O.Scene(s.tris.view(O.TRI_DTYPE), O.ACCEL_BVH)
+    v, ov = R.main_viewport(960, 540, 5, 1), O.main_viewport(960, 540, 5, 1)
+    assert_bit_exact(gpu_render(R, s, v, seed=3), osc.render(ov, seed=3), "teapot field")
+    s.release()
+
+
 def test_stats_variant_and_bvh_shape(R, scenes):
     s = scenes[False][0]
     inf = s.info()
@@ -244,6 +258,40 @@ def test_multi_gpu_tiles_identical(R, scenes):
     many = gpu_render(R, s2, v, seed=6, threads=n)
     assert np.array_equal(one[1], many[1]) and np.array_equal(bits(one[0]), bits(many[0]))
     assert one[3].total_rays == many[3].total_rays
+
+
+def test_sample_range_sum_only_bit_exact(R, O, scenes):
+    """The per-rank piece of the sample-partitioned mode (torchrun): samples [b, e) of spp with RTB_FLAG_SUM_ONLY
+    into a device buffer; must equal the oracle's partial sum bit for bit, and reduce + rtb_scale_device must
+    reproduce the single-process frame to rounding."""
+    import torch
+    from rust_raytrace_b200 import _lib, dist as RD
+    s, _, bvh = scenes[False]
+    W, H, spp, world = 200, 120, 6, 4
+    L = _lib.lib()
+    _lib.check(L.rtb_init(1, None), "rtb_init")
+    h = s.upload()
+    v = R.main_viewport(W, H, 5, spp)
+    v.seed = 21
+    ov = O.main_viewport(W, H, 5, spp)
+    total = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    rays = 0
+    for rank in range(world):
+        sv = RD.sample_view(v, rank, world)
+        buf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        st = _lib.RtbStats()
+        _lib.check(L.rtb_render_device(h, C.byref(sv), 0, 0, 1, buf.data_ptr(), None, None, None, C.byref(st)), "render")
+        ref, ost = bvh.render_samples(ov, sv.sample_begin, sv.sample_end, seed=21)
+        assert np.array_equal(bits(buf.cpu().numpy()), bits(ref)), f"partial sum of rank {rank} differs"
+        assert st.rays == ost.rays
+        rays += st.rays
+        total += buf
+    out = RD.reduce_samples(total, spp)
+    torch.cuda.synchronize()
+    full = bvh.render(ov, seed=21)
+    assert rays == full[3].rays
+    got = out.cpu().numpy()
+    assert np.all(got[..., 3] == 0) and np.max(np.abs(got - full[0])) < 1e-6
 
 
 def test_progressive_psnr(R, O, scenes):

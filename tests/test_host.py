@@ -23,11 +23,30 @@ def test_library_exports_every_declared_symbol(R):
         assert getattr(L, name) is not None
 
 
-def test_struct_sizes_match_the_header(R):
+def test_struct_sizes_match_the_header(R, tmp_path):
+    """The ctypes mirrors against the real header: a C program compiled with gcc from include/rtb.h prints sizeof /
+    offsetof of every ABI struct."""
+    import os
+    import subprocess
     from rust_raytrace_b200 import _lib
-    assert _lib.TRI_DTYPE.itemsize == 140
-    assert C.sizeof(_lib.RtbView) == 88
-    assert C.sizeof(_lib.RtbStats) == 48
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "rtb.h"
+#include "rtb_host.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(RtbTriangle), sizeof(RtbView), sizeof(RtbStats), sizeof(RtbSceneInfo),
+           sizeof(RtbSurface), offsetof(RtbView, seed), offsetof(RtbStats, ms_stage), offsetof(RtbSceneInfo, ms_upload));
+    return 0;
+}''')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [_lib.TRI_DTYPE.itemsize, C.sizeof(_lib.RtbView), C.sizeof(_lib.RtbStats), C.sizeof(_lib.RtbSceneInfo),
+            C.sizeof(_lib.RtbSurface), _lib.RtbView.seed.offset, _lib.RtbStats.ms_stage.offset, _lib.RtbSceneInfo.ms_upload.offset]
+    assert got == want, (got, want)
+    assert got[0] == 140 and got[1] == 88
 
 
 def test_main_scene_bytes_equal_oracle(R, O, teapot_mesh):
