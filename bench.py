@@ -209,8 +209,12 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # CPU-side barrier for the e2e leg: an NCCL barrier parks a spinning kernel on every waiting rank's GPU,
+        # which would compete with the kernels rank 0 launches on those GPUs while it drives all N of them
+        host_group = dist.new_group(backend="gloo")
 
     import rust_raytrace_b200 as R
     from rust_raytrace_b200 import _lib, dist as RD
@@ -320,7 +324,8 @@ def run_gpu(args):
     # ---- e2e through the public API with host buffers (rank 0 drives all N GPUs) ----
     e2e = None
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
     if rank == 0:
         ids = (C.c_int * args.gpus)(*range(args.gpus))
         scene.release()
@@ -348,7 +353,7 @@ def run_gpu(args):
         assert int(caster.stats.rays) == int(total_rays), (caster.stats.rays, total_rays)
         sc_all.release()
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = measured_peaks()

@@ -183,6 +183,9 @@ pub struct B200RayCaster {
     /// samples of a multi-spp frame are partitioned over the GPUs and reduced over NVLink (rtb_render_progressive)
     pub progressive: bool,
     cache: Mutex<Option<Uploaded>>,
+    /// (address, bytes) of the caller's image buffer currently pinned with rtb_host_register: pinning 133 MB costs
+    /// milliseconds, so it is done once per buffer, not once per frame
+    pinned: Mutex<Option<(usize, usize)>>,
 }
 
 unsafe impl Send for B200RayCaster {}
@@ -190,7 +193,7 @@ unsafe impl Sync for B200RayCaster {}
 
 impl B200RayCaster {
     pub fn new() -> Self {
-        B200RayCaster { seed: 0, progressive: false, cache: Mutex::new(None) }
+        B200RayCaster { seed: 0, progressive: false, cache: Mutex::new(None), pinned: Mutex::new(None) }
     }
 
     fn scene_handle(&self, s: &Scene, n_gpus: usize) -> Result<*mut RtbSceneOpaque, String> {
@@ -219,8 +222,26 @@ impl B200RayCaster {
     }
 }
 
+impl B200RayCaster {
+    fn pin(&self, ptr: *mut c_void, bytes: usize) {
+        let mut p = self.pinned.lock().unwrap();
+        if *p == Some((ptr as usize, bytes)) {
+            return;
+        }
+        if let Some((old, _)) = p.take() {
+            unsafe { rtb_host_unregister(old as *mut c_void) };
+        }
+        if unsafe { rtb_host_register(ptr, bytes) } == 0 {      // failure only costs D2H speed
+            *p = Some((ptr as usize, bytes));
+        }
+    }
+}
+
 impl Drop for B200RayCaster {
     fn drop(&mut self) {
+        if let Some((old, _)) = self.pinned.lock().unwrap().take() {
+            unsafe { rtb_host_unregister(old as *mut c_void) };
+        }
         if let Some(u) = self.cache.lock().unwrap().take() {
             unsafe { rtb_scene_destroy(u.handle) };
         }
@@ -237,14 +258,13 @@ impl RayCaster for B200RayCaster {
         let mut st = RtbStats::default();
         let bytes = data.len() * 16;
         let p = data.as_mut_ptr() as *mut f32;
+        self.pin(p as *mut c_void, bytes);
         unsafe {
-            rtb_host_register(p as *mut c_void, bytes);      // pinned D2H; failure only costs speed
             let rc = if self.progressive && view.spp > 1 {
                 rtb_render_progressive(h, &view, p, &mut st)
             } else {
                 rtb_render(h, &view, p, std::ptr::null_mut(), std::ptr::null_mut(), &mut st)
             };
-            rtb_host_unregister(p as *mut c_void);
             if rc != 0 {
                 panic!("b200: rtb_render failed: {}", last_error());   // the reference's error convention (unwrap)
             }
