@@ -31,19 +31,18 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t INVALID_SLOT = 0xffffffffu;
 constexpr uint32_t LEAF_FLAG = 0x80000000u;
-constexpr uint32_t WF_CHUNK = 128;      // rays reserved per warp per global atomic
 constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent kernels
 constexpr int WF_OVF = 3 * (RTB_STACK / 2 + 1) + 2;   // worst-case BVH4 stack (tree height < RTB_STACK), thread-local overflow part
 constexpr int WF_SMEM_STACK = 8;        // stack entries per thread kept in shared memory
 #ifndef WF_BOUNCE_MIN_BLOCKS
 #define WF_BOUNCE_MIN_BLOCKS 8          // 64 registers: 32 warps/SM instead of 24 at the natural 80
 #endif
-// Tunables (env RTB_WF_DESCEND / RTB_WF_REFILL override for experiments).  Measured on B200, 4K teapot frame, with
-// one trace kernel per bounce level: (descend, refill) = (2,4) 3.53 ms, (4,8) 3.15 ms, (8,16) 3.06 ms,
-// (unbounded,16) 3.30 ms.  Retiring surplus warps on small queues made things worse in proportion (the deep
-// levels are latency-, not issue-bound).
+// Tunables (env RTB_WF_DESCEND / RTB_WF_REFILL override for experiments).  Measured on B200, 4K teapot frame, current
+// pipeline with exact work fetch: (descend, refill) = (4,16) 2.82 ms, (4,20) 2.79, (4,24) 2.80, (4,28) 2.86,
+// (3,20) 2.79, (6,20) 2.87, (8,20) 2.90.
 constexpr uint32_t WF_DESCEND_MAX = 4;  // BVH4 node visits per lane per round before leaves are processed
-constexpr uint32_t WF_REFILL_MIN = 16;  // service (shade / refill) lanes once at least this many wait
+constexpr uint32_t WF_REFILL_MIN = 20;  // service (shade / refill) lanes once at least this many wait
+struct WfTune { uint32_t descend_max, refill_min; int smem_depth; };
 
 // slot -> pixel.  Slots enumerate 8x4 warp tiles inside the 8-row bands this launch renders.
 struct Pixel { uint32_t row, col, out_idx; bool inside; };
@@ -223,23 +222,21 @@ __device__ __forceinline__ void brute_scan(const SceneDev& sc, TravState& s, uns
     }
 }
 
-// Warp-level work fetch: lanes in `need` get consecutive queue indices; one global atomic per WF_CHUNK rays.
+// Warp-level work fetch: the lanes in `need` take consecutive queue indices, ONE global atomic per refill that
+// reserves exactly popc(need) rays.  Reserving a fixed portion per warp instead (128 rays per atomic at first) left
+// the kernel waiting for the warps that happened to draw one portion more: on B200, 4K teapot frame, 128 rays per
+// fetch 3.18 ms, 32 rays 2.99 ms, exact 2.95 ms; on a 1/8 band share of the frame 0.97 / 0.58 / 0.52 ms.
 struct WorkFetch {
-    uint32_t chunk_next = 0, chunk_end = 0;   // warp-uniform
     bool exhausted = false;
     // returns this lane's queue index or 0xffffffff
     __device__ __forceinline__ uint32_t fetch(unsigned need, bool me, uint32_t n, uint32_t* counter, unsigned lane) {
         if (exhausted || need == 0u) return 0xffffffffu;
-        if (chunk_next >= chunk_end) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(counter, WF_CHUNK);
-            base = __shfl_sync(FULL, base, 0);
-            if (base >= n) { exhausted = true; return 0xffffffffu; }
-            chunk_next = base; chunk_end = min(base + WF_CHUNK, n);
-        }
-        const uint32_t idx = chunk_next + __popc(need & ((1u << lane) - 1u));
-        chunk_next = min(chunk_next + (uint32_t)__popc(need), chunk_end);
-        return (me && idx < chunk_end) ? idx : 0xffffffffu;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(need));
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) { exhausted = true; return 0xffffffffu; }
+        const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
+        return (me && idx < n) ? idx : 0xffffffffu;
     }
 };
 
@@ -249,8 +246,10 @@ struct WorkFetch {
 template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK, 4)
 k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __restrict__ qd, uint32_t n,
-           float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max,
-           uint32_t refill_min, int smem_depth, TraceCounters* __restrict__ counters) {
+           float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, const WfTune tune,
+           TraceCounters* __restrict__ counters) {
+    const uint32_t descend_max = tune.descend_max, refill_min = tune.refill_min;
+    const int smem_depth = tune.smem_depth;
     extern __shared__ uint32_t smem_stack[];
     uint32_t* const stack = smem_stack + threadIdx.x;     // entry k lives at stack[k * WF_BLOCK]
     uint32_t ovf[WF_OVF];
@@ -404,8 +403,10 @@ template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK, WF_BOUNCE_MIN_BLOCKS)
 k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const float4* __restrict__ qo,
             const float4* __restrict__ qd, const uint32_t* __restrict__ n_ptr, uint32_t smp,
-            uint32_t* __restrict__ work_counter, uint32_t brute, uint32_t descend_max, uint32_t refill_min,
-            int smem_depth, TraceCounters* __restrict__ counters) {
+            uint32_t* __restrict__ work_counter, uint32_t brute, const WfTune tune,
+            TraceCounters* __restrict__ counters) {
+    const uint32_t descend_max = tune.descend_max, refill_min = tune.refill_min;
+    const int smem_depth = tune.smem_depth;
     extern __shared__ uint32_t smem_stack[];
     uint32_t* const stack = smem_stack + threadIdx.x;
     uint32_t ovf[WF_OVF];
@@ -568,6 +569,7 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
         refill_min = e2 ? (uint32_t)std::min(32, std::max(1, atoi(e2))) : WF_REFILL_MIN;
     }
 
+    const WfTune tune = {descend_max, refill_min, smem_depth};
     RTB_CUDA(cudaMemsetAsync(wc, 0, sizeof(WfCounters), stream));
     auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], stream); };
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
@@ -575,18 +577,18 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
         k_wf_raygen<<<(n_slots + 255u) / 256u, 256, 0, stream>>>(vw, smp, n_slots, qo0, qd0, pb.rng_state);
         mark(1);
         if (stats)
-            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, smem_depth, d_counters);
+            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
         else
-            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, descend_max, refill_min, smem_depth, d_counters);
+            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
         mark(2);
         k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, qo0, qd0, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
         mark(3);
         if (launches) *launches += 3;
         if (vw.maxdepth > 1) {
             if (stats)
-                k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, smem_depth, d_counters);
+                k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
             else
-                k_wf_bounce<false><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, descend_max, refill_min, smem_depth, d_counters);
+                k_wf_bounce<false><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
             if (launches) ++*launches;
         }
         mark(4);
