@@ -4,10 +4,10 @@
 // (ncu, profiles/r1_v1_*): rays of one warp leave the scene at different times and the surviving
 // Matte/mirror paths bounce up to maxdepth times.  Here the same arithmetic is split into stages:
 //
-//   k_wf_raygen   one thread per pixel slot: Viewport::pixel_ray (raytrace.rs:1374-1394) -> ray queue 0
-//   k_wf_trace    PERSISTENT kernel over the coherent primary rays: warps pull rays from the queue, every
-//                 lane that finishes its ray is refilled (ballot + one atomic per 128 rays per warp), so the
-//                 traversal loop runs with ~25 of 32 lanes; closest hit -> hit record
+//   (raygen)      Viewport::pixel_ray (raytrace.rs:1374-1394), generated in place by the two kernels below
+//   k_wf_trace    PERSISTENT kernel over the coherent primary rays: warps pull pixel slots, every lane that
+//                 finishes its ray is refilled (ballot + one atomic per refill), so the traversal loop runs
+//                 with ~27 of 32 lanes; closest hit -> hit record
 //   k_wf_shade    one thread per primary ray: Triangle::intersects classification, color_ray (:1199-1254):
 //                 terminal paths add their sample to the pixel; bouncing paths push (colour, alpha) on the
 //                 pixel's mix stack and append the bounce ray to the bounce queue (warp-aggregated atomic)
@@ -18,7 +18,7 @@
 //                 per level however few rays it holds) and ran with 9-16 of 32 lanes.
 //   k_wf_tally    per-sample counter reset
 //
-// Per-pixel state lives in HBM between stages (ray 32 B, hit 8 B, mix stack 16 B/level, RNG 8 B).
+// Per-pixel state lives in HBM between stages (hit 8 B, bounce ray 32 B, mix stack 16 B/level, RNG 8 B).
 #include <algorithm>
 #include <cstdlib>
 
@@ -64,27 +64,21 @@ __device__ __forceinline__ Pixel slot_to_pixel(const ViewDev& vw, uint32_t slot)
 }
 
 // ---------------------------------------------------------------------------
-// stage 0: primary rays
+// stage 0: primary rays.  Not a kernel of its own any more: the trace kernel generates a slot's ray when a lane
+// takes the slot, and the shade kernel regenerates it (same arithmetic, same RNG draws, ~80 instructions) instead
+// of reading it back.  A separate raygen kernel cost 0.08 ms of the 4K frame plus 64 B per pixel written to and
+// read from HBM twice.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wf_raygen(const ViewDev vw, uint32_t smp, uint32_t n_slots,
-                                                   float4* __restrict__ qo, float4* __restrict__ qd,
-                                                   uint64_t* __restrict__ rng_state) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
+__device__ __forceinline__ bool primary_ray(const ViewDev& vw, uint32_t slot, uint32_t smp, V3* o, V3* d, Rng* g,
+                                            Pixel* px_out) {
     const Pixel px = slot_to_pixel(vw, slot);
-    if (!px.inside) {
-        qo[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(INVALID_SLOT));
-        return;
-    }
-    Rng g;
-    g.seed(vw.seed, (uint64_t)px.row * vw.width + px.col, smp);
+    *px_out = px;
+    if (!px.inside) return false;
+    g->seed(vw.seed, (uint64_t)px.row * vw.width + px.col, smp);
     float u_off = 0.5f, v_off = 0.5f;
-    if (vw.spp != 1) { u_off = g.next_f32(); v_off = g.next_f32(); }   // :1382-1386
-    V3 o, d;
-    gen_primary(vw, px.row, px.col, u_off, v_off, &o, &d);
-    qo[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(slot));
-    qd[slot] = make_float4(d.x, d.y, d.z, 0.f);
-    rng_state[slot] = g.state;
+    if (vw.spp != 1) { u_off = g->next_f32(); v_off = g->next_f32(); }   // :1382-1386
+    gen_primary(vw, px.row, px.col, u_off, v_off, o, d);
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -245,7 +239,7 @@ struct WorkFetch {
 // ---------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK, 4)
-k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __restrict__ qd, uint32_t n,
+k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
            float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, const WfTune tune,
            TraceCounters* __restrict__ counters) {
     const uint32_t descend_max = tune.descend_max, refill_min = tune.refill_min;
@@ -268,11 +262,10 @@ k_wf_trace(const SceneDev sc, const float4* __restrict__ qo, const float4* __res
         if (!wf.exhausted && (uint32_t)__popc(need) >= refill_min) {
             const uint32_t idx = wf.fetch(need, !trav, n, work_counter, lane);
             if (idx != 0xffffffffu) {
-                const float4 ro = __ldcs(qo + idx);      // streamed once: keep it out of L1
-                if (__float_as_uint(ro.w) != INVALID_SLOT) {
-                    const float4 rd = __ldcs(qd + idx);
+                V3 o, d; Rng g; Pixel px;
+                if (primary_ray(vw, idx, smp, &o, &d, &g, &px)) {   // slots outside the image have no ray
                     ray_id = idx;
-                    start_ray(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), root_code);
+                    start_ray(s, o, d, root_code);
                     trav = true;
                 }
             }
@@ -336,7 +329,6 @@ __device__ __forceinline__ void finish_path(const ViewDev& vw, const PathBuffers
 // stage 2: shade the primary hits, emit the bounce queue
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const ViewDev vw, const PathBuffers pb,
-                                                  const float4* __restrict__ qo_in, const float4* __restrict__ qd_in,
                                                   const float2* __restrict__ hit, uint32_t n, uint32_t smp,
                                                   float4* __restrict__ qo_out, float4* __restrict__ qd_out,
                                                   uint32_t* __restrict__ n_out) {
@@ -346,27 +338,23 @@ __global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const ViewD
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool emit = false;
         V3 no = mk(0.f, 0.f, 0.f), nd = mk(0.f, 0.f, 0.f);
-        uint32_t slot = INVALID_SLOT;
-        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) { ro = __ldcs(qo_in + i); slot = __float_as_uint(ro.w); }
-        if (slot != INVALID_SLOT) {
-            const float4 rd = __ldcs(qd_in + i);
-            const V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
+        const uint32_t slot = i;
+        V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, 0.f);
+        Rng g; g.state = 0;
+        Pixel px; px.inside = false;
+        if (i < n && primary_ray(vw, slot, smp, &o, &d, &g, &px)) {
             const float2 hr = __ldcs(hit + i);
             const int prim_slot = __float_as_int(hr.y);
             const float t = hr.x;
             V3 term = mk(0.f, 0.f, 0.f);
             uint32_t levels = 0;
             if (smp == 0u && (pb.prim_out || pb.t_out)) {
-                const Pixel px = slot_to_pixel(vw, slot);
                 if (pb.prim_out) pb.prim_out[px.out_idx] = prim_slot >= 0 ? __float_as_uint(__ldg(sc.tri + (size_t)RTB_TRI_F4 * prim_slot + 1).w) : 0u;
                 if (pb.t_out) pb.t_out[px.out_idx] = prim_slot >= 0 ? t : 0.0f;
             }
             if (prim_slot < 0) {
                 term = sky_color();                                            // project_ray miss :1284
             } else {
-                Rng g;
-                g.state = pb.rng_state[slot];
                 V3 color;
                 float alpha = 0.f;
                 if (shade_hit(sc, prim_slot, t, o, d, g, &color, &alpha, &no, &nd) == 0) {
@@ -507,7 +495,7 @@ __global__ void k_wf_tally(WfCounters* c) {
 // ---------------------------------------------------------------------------
 size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample) {
     size_t b = 0;
-    b += 4 * (sizeof(float4) * (size_t)n_slots + 256);          // primary + bounce ray queues (o, d)
+    b += 2 * (sizeof(float4) * (size_t)n_slots + 256);          // bounce ray queue (o, d)
     b += sizeof(float2) * (size_t)n_slots + 256;                // hit records of the primary rays
     b += sizeof(float4) * (size_t)n_slots * maxdepth + 256;     // mix stacks
     b += sizeof(uint64_t) * (size_t)n_slots + 256;              // RNG
@@ -526,7 +514,6 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     // carve the workspace
     char* p = (char*)workspace;
     auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
-    float4* qo0 = (float4*)take(sizeof(float4) * n_slots); float4* qd0 = (float4*)take(sizeof(float4) * n_slots);
     float4* qo1 = (float4*)take(sizeof(float4) * n_slots); float4* qd1 = (float4*)take(sizeof(float4) * n_slots);
     float2* hit = (float2*)take(sizeof(float2) * n_slots);
     PathBuffers pb;
@@ -574,16 +561,15 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], stream); };
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
         mark(0);
-        k_wf_raygen<<<(n_slots + 255u) / 256u, 256, 0, stream>>>(vw, smp, n_slots, qo0, qd0, pb.rng_state);
         mark(1);
         if (stats)
-            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
+            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
         else
-            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, qo0, qd0, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
+            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
         mark(2);
-        k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, qo0, qd0, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
+        k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
         mark(3);
-        if (launches) *launches += 3;
+        if (launches) *launches += 2;
         if (vw.maxdepth > 1) {
             if (stats)
                 k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
