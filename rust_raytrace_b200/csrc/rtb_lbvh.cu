@@ -14,7 +14,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "rtb_internal.cuh"
 
@@ -142,6 +144,143 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __re
     if (i == 0) parent[0] = -1;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// PLOC — parallel locally-ordered clustering (Meister & Bittner 2018) on the Morton-sorted primitives: the
+// default topology builder.  Clusters sit in Morton order; every cluster looks PLOC_R places left and right for the
+// neighbour whose union box has the smallest surface area; mutual nearest neighbours merge into a new node; the
+// array is compacted; repeat until one cluster is left.  Compared with the plain radix tree (k_hierarchy) the result
+// needs 14 % fewer BVH4 node visits per bounce ray on the teapot scene and 22-25 % fewer on the 1 M-triangle field
+// (CPU experiment tools/experiments/bvh_quality.cpp; a full binned-SAH build gets 15 % / 37 %).
+//
+// PLOC node ids: leaves 0..n-1 (Morton order), internal n..2n-2 in creation order, root = 2n-2.  k_ploc_finish
+// relabels to the convention the rest of the builder uses (internal 0..n-2 with root 0, leaf n-1+k where k is now
+// the DFS position), so that every node again covers a contiguous primitive range.
+// ---------------------------------------------------------------------------------------------------------
+struct PlocState { uint32_t m; uint32_t n_internal; };
+
+__device__ __forceinline__ float union_area(float4 al, float4 ah, float4 bl, float4 bh) {
+    const float dx = fmaxf(ah.x, bh.x) - fminf(al.x, bl.x);
+    const float dy = fmaxf(ah.y, bh.y) - fminf(al.y, bl.y);
+    const float dz = fmaxf(ah.z, bh.z) - fminf(al.z, bl.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_ploc_init(uint32_t n, const uint32_t* __restrict__ sorted_vals, const float4* __restrict__ plo,
+                            const float4* __restrict__ phi, float4* __restrict__ lo, float4* __restrict__ hi,
+                            uint32_t* __restrict__ cluster, uint32_t* __restrict__ size, int* __restrict__ parent,
+                            PlocState* st) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) { st->m = n; st->n_internal = 0u; }
+    if (k >= n) return;
+    const uint32_t prim = sorted_vals[k];
+    lo[k] = plo[prim]; hi[k] = phi[prim];
+    cluster[k] = k; size[k] = 1u; parent[k] = -1;
+}
+
+constexpr int PLOC_BLOCK = 256;
+constexpr int PLOC_R_MAX = 32;
+
+// nearest neighbour of every cluster within +-R places; the candidate boxes of a block are staged in shared memory
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nn(const uint32_t* __restrict__ cluster, const PlocState* st,
+                                                       const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                       int R, uint32_t* __restrict__ nn) {
+    __shared__ float4 slo[PLOC_BLOCK + 2 * PLOC_R_MAX], shi[PLOC_BLOCK + 2 * PLOC_R_MAX];
+    const int m = (int)st->m;
+    const int b0 = blockIdx.x * PLOC_BLOCK;
+    if (b0 >= m) return;
+    for (int t = threadIdx.x; t < PLOC_BLOCK + 2 * R; t += PLOC_BLOCK) {
+        const int j = b0 - R + t;
+        if (j >= 0 && j < m) { const uint32_t c = cluster[j]; slo[t] = lo[c]; shi[t] = hi[c]; }
+    }
+    __syncthreads();
+    const int i = b0 + threadIdx.x;
+    if (i >= m) return;
+    const float4 al = slo[threadIdx.x + R], ah = shi[threadIdx.x + R];
+    float best = FLT_MAX;
+    int bj = -1;
+    for (int j = max(0, i - R); j <= min(m - 1, i + R); ++j) {
+        if (j == i) continue;
+        const int t = j - b0 + R;
+        const float a = union_area(al, ah, slo[t], shi[t]);
+        if (a < best) { best = a; bj = j; }       // ties: the lowest index
+    }
+    nn[i] = (uint32_t)bj;
+}
+
+// flags for the compaction scan: low word = "stays in the array", high word = "creates a node"
+__global__ void k_ploc_flags(const uint32_t* __restrict__ nn, const PlocState* st, unsigned long long* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m = st->m;
+    if (i >= m) return;
+    const uint32_t j = nn[i];
+    const bool mutual = (j < m) && nn[j] == i;
+    flags[i] = mutual ? (i < j ? ((1ull << 32) | 1ull) : 0ull) : 1ull;
+}
+
+__global__ void k_ploc_apply(uint32_t n, const uint32_t* __restrict__ cin, const uint32_t* __restrict__ nn,
+                             const unsigned long long* __restrict__ pos, PlocState* st, uint32_t* __restrict__ cout,
+                             int2* __restrict__ pchildren, int* __restrict__ parent, float4* __restrict__ lo,
+                             float4* __restrict__ hi, uint32_t* __restrict__ size, uint32_t m, uint32_t base) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t j = nn[i];
+    const bool mutual = (j < m) && nn[j] == i;
+    const unsigned long long p = pos[i];
+    const uint32_t out = (uint32_t)p, created = (uint32_t)(p >> 32);
+    uint32_t keeps = 1u, creates = 0u;
+    if (mutual) {
+        if (i < j) {
+            const uint32_t a = cin[i], b = cin[j];
+            const uint32_t id = n + base + created;
+            pchildren[id - n] = make_int2((int)a, (int)b);
+            parent[a] = (int)id; parent[b] = (int)id; parent[id] = -1;
+            const float4 al = lo[a], ah = hi[a], bl = lo[b], bh = hi[b];
+            lo[id] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
+            hi[id] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+            size[id] = size[a] + size[b];
+            cout[out] = id;
+            creates = 1u;
+        } else {
+            keeps = 0u;
+        }
+    } else {
+        cout[out] = cin[i];
+    }
+    if (i == m - 1) { st->m = out + keeps; st->n_internal = base + created + creates; }
+}
+
+// PLOC ids -> the builder's node convention + DFS primitive order.  One thread per internal PLOC node.
+__global__ void k_ploc_finish(uint32_t n, const int2* __restrict__ pchildren, const int* __restrict__ pparent,
+                              const uint32_t* __restrict__ size, const uint32_t* __restrict__ sorted_vals,
+                              int2* __restrict__ children, int2* __restrict__ range, int* __restrict__ parent,
+                              uint32_t* __restrict__ vals_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n - 1) return;
+    const uint32_t x = n + t;
+    // DFS offset of x: sizes of the left siblings on the way to the root
+    uint32_t off = 0;
+    for (uint32_t c = x;;) {
+        const int p = pparent[c];
+        if (p < 0) break;
+        const int2 ch = pchildren[(uint32_t)p - n];
+        if ((uint32_t)ch.y == c) off += size[ch.x];
+        c = (uint32_t)p;
+    }
+    const int2 ch = pchildren[t];
+    const uint32_t l = (uint32_t)ch.x, r = (uint32_t)ch.y;
+    const uint32_t off_l = off, off_r = off + size[l];
+    const int kid = (int)(2u * n - 2u - x);
+    const int kl = l < n ? (int)(n - 1u + off_l) : (int)(2u * n - 2u - l);
+    const int kr = r < n ? (int)(n - 1u + off_r) : (int)(2u * n - 2u - r);
+    children[kid] = make_int2(kl, kr);
+    range[kid] = make_int2((int)off, (int)(off + size[x] - 1u));
+    parent[kl] = kid; parent[kr] = kid;
+    if (kid == 0) parent[0] = -1;
+    if (l < n) vals_out[off_l] = sorted_vals[l];
+    if (r < n) vals_out[off_r] = sorted_vals[r];
+}
+
 // Bottom-up refit.  blo/bhi are indexed by Karras node id (internal 0..n-2, leaf n-1+k).
 __global__ void k_refit(const float4* __restrict__ plo, const float4* __restrict__ phi,
                         const uint32_t* __restrict__ sorted_vals, int n, const int2* __restrict__ children,
@@ -181,10 +320,47 @@ __global__ void k_leaf_depth(int n, const int* __restrict__ parent, BuildScratch
     if ((threadIdx.x & 31) == 0) atomicMax(&s->height, depth);
 }
 
-__global__ void k_split_flags(const int2* __restrict__ range, int n_internal, uint32_t* __restrict__ flags) {
+// What becomes of every node of the binary tree when subtrees of <= RTB_LEAF_MAX primitives are collapsed into
+// leaves.  A small subtree is collapsed unless the surface-area heuristic prefers to keep its top split
+// (cost of one more box test, 1 x A(node), against the triangle tests it saves: A(l)|l| + A(r)|r| vs A(node)|node|);
+// on the teapot scene that rule trades +3 % node visits for -17 % exact triangle tests, on the 1 M field -50 %.
+enum : uint8_t { KIND_INTERNAL = 0, KIND_LEAF = 1, KIND_SWALLOWED = 2 };
+
+__device__ __forceinline__ float box_area(float4 l, float4 h) {
+    const float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ bool collapses(int c, int n, const int2* __restrict__ children, const int2* __restrict__ range,
+                                          const float4* __restrict__ blo, const float4* __restrict__ bhi, int sah) {
+    if (c >= n - 1) return true;                                   // a single primitive
+    const int size = range[c].y - range[c].x + 1;
+    if (size > RTB_LEAF_MAX) return false;
+    if (!sah) return true;
+    const int2 ch = children[c];
+    const int sl = ch.x >= n - 1 ? 1 : range[ch.x].y - range[ch.x].x + 1;
+    const int sr = ch.y >= n - 1 ? 1 : range[ch.y].y - range[ch.y].x + 1;
+    const float a = box_area(blo[c], bhi[c]);
+    const float split = a + box_area(blo[ch.x], bhi[ch.x]) * (float)sl + box_area(blo[ch.y], bhi[ch.y]) * (float)sr;
+    return !(split < a * (float)size);
+}
+
+__global__ void k_node_kind(int n, const int2* __restrict__ children, const int2* __restrict__ range,
+                            const int* __restrict__ parent, const float4* __restrict__ blo,
+                            const float4* __restrict__ bhi, int sah, uint8_t* __restrict__ kind) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 2 * n - 1) return;
+    // swallowed iff some ancestor collapses; only ancestors of <= RTB_LEAF_MAX primitives can
+    bool swallowed = false;
+    for (int p = parent[c]; p >= 0 && (range[p].y - range[p].x + 1) <= RTB_LEAF_MAX; p = parent[p])
+        if (collapses(p, n, children, range, blo, bhi, sah)) { swallowed = true; break; }
+    kind[c] = swallowed ? KIND_SWALLOWED : (collapses(c, n, children, range, blo, bhi, sah) ? KIND_LEAF : KIND_INTERNAL);
+}
+
+__global__ void k_split_flags(const uint8_t* __restrict__ kind, int n_internal, uint32_t* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_internal) return;
-    flags[i] = (range[i].y - range[i].x + 1) > RTB_LEAF_MAX ? 1u : 0u;
+    flags[i] = kind[i] == KIND_INTERNAL ? 1u : 0u;
 }
 
 __device__ __forceinline__ void write_node(float4* nodes, uint32_t pos, float4 lo, float4 hi, float pad, uint32_t a,
@@ -198,10 +374,11 @@ __device__ __forceinline__ void write_node(float4* nodes, uint32_t pos, float4 l
 __global__ void k_emit_nodes(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                              const int* __restrict__ parent, const float4* __restrict__ blo,
                              const float4* __restrict__ bhi, const uint32_t* __restrict__ slot,
-                             float4* __restrict__ nodes, BuildScratch* s) {
+                             const uint8_t* __restrict__ kind, float4* __restrict__ nodes, BuildScratch* s) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     int total = 2 * n - 1;
     if (c >= total) return;
+    if (kind[c] == KIND_SWALLOWED) return;                      // inside a collapsed leaf
     const float pad = o2f(s->max_abs) * (1.0f / 131072.0f);   // 2^-17 of the largest |coordinate|
     int first, count;
     if (c >= n - 1) { first = c - (n - 1); count = 1; }
@@ -210,11 +387,9 @@ __global__ void k_emit_nodes(int n, const int2* __restrict__ children, const int
     if (c == 0) pos = 0;
     else {
         int p = parent[c];
-        int psize = range[p].y - range[p].x + 1;
-        if (psize <= RTB_LEAF_MAX) return;   // swallowed by a collapsed leaf
         pos = 2u + 2u * slot[p] + (children[p].y == c ? 1u : 0u);
     }
-    if (count <= RTB_LEAF_MAX) {
+    if (kind[c] == KIND_LEAF) {
         write_node(nodes, pos, blo[c], bhi[c], pad, (uint32_t)first, (uint32_t)count);
         atomicMax(&s->max_leaf, (uint32_t)count);
         atomicAdd(&s->n_leaves, 1u);
@@ -233,14 +408,13 @@ __global__ void k_emit_nodes(int n, const int2* __restrict__ children, const int
 // itself where that child is already a leaf.  Node = 8 x float4 (128 B, one cache line), SoA over the
 // entries: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] code[4] pad.  code: 0 = empty slot,
 // 0x80000000 | first<<3 | count = leaf, otherwise the index of the child BVH4 node.
-__global__ void k_flag4(int n_internal, const int2* __restrict__ range, const int* __restrict__ parent,
+__global__ void k_flag4(int n_internal, const uint8_t* __restrict__ kind, const int* __restrict__ parent,
                         uint32_t* __restrict__ flags4, BuildScratch* s) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_internal) return;
     uint32_t depth = 0;
     for (int p = parent[i]; p >= 0; p = parent[p]) ++depth;
-    const int size = range[i].y - range[i].x + 1;
-    const bool kept = (i == 0) || (size > RTB_LEAF_MAX && (depth & 1u) == 0u);
+    const bool kept = (i == 0) || (kind[i] == KIND_INTERNAL && (depth & 1u) == 0u);
     flags4[i] = kept ? 1u : 0u;
     if (kept) atomicMax(&s->depth4, depth >> 1);
 }
@@ -248,13 +422,14 @@ __global__ void k_flag4(int n_internal, const int2* __restrict__ range, const in
 __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                               const float4* __restrict__ blo, const float4* __restrict__ bhi,
                               const uint32_t* __restrict__ flags4, const uint32_t* __restrict__ idx4,
-                              float4* __restrict__ nodes4, const BuildScratch* __restrict__ s) {
+                              const uint8_t* __restrict__ kind, float4* __restrict__ nodes4,
+                              const BuildScratch* __restrict__ s) {
     const int n_internal = n - 1;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_internal > 0 ? n_internal : 1)) return;
     if (n_internal > 0 && !flags4[i]) return;
     const float pad = o2f(s->max_abs) * (1.0f / 131072.0f);
-    auto leaf_final = [&](int c) { return c >= n - 1 || (range[c].y - range[c].x + 1) <= RTB_LEAF_MAX; };
+    auto leaf_final = [&](int c) { return kind[c] == KIND_LEAF; };
     int ent[4];
     int n_ent = 0;
     if (n_internal == 0) ent[n_ent++] = 0;                       // the single Karras leaf
@@ -327,8 +502,29 @@ inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 }  // namespace
 
+static void free_result(BuildResult* r) {
+    cudaFree(r->d_nodes); cudaFree(r->d_nodes4); cudaFree(r->d_tri); cudaFree(r->d_shade); cudaFree(r->d_prim_order);
+    *r = BuildResult();
+}
+
+static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n, cudaStream_t stream,
+                      bool force_karras, BuildResult* out);
+
 int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n, cudaStream_t stream,
                    BuildResult* out) {
+    int rc = build_impl(d_tris, d_keep, n, stream, false, out);
+    if (rc == RTB_ERR_INVALID && out->tree_height + 2 > RTB_STACK) {
+        // a PLOC tree can, on adversarial input, come out deeper than the traversal stack allows: the radix tree
+        // over 63-bit codes cannot (height <= 63 + log2 of the largest run of equal codes)
+        free_result(out);
+        rc = build_impl(d_tris, d_keep, n, stream, true, out);
+    }
+    if (rc != RTB_OK) free_result(out);
+    return rc;
+}
+
+static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n, cudaStream_t stream,
+                      bool force_karras, BuildResult* out) {
     *out = BuildResult();
     cudaEvent_t e0, e1;
     RTB_CUDA(cudaEventCreate(&e0));
@@ -361,7 +557,14 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     DevBuf<uint32_t> vals, vals_sorted, arrive, flags, slot, flags4, idx4;
     DevBuf<int2> children, range;
     DevBuf<int> parent;
-    DevBuf<uint8_t> cub_tmp;
+    DevBuf<uint8_t> cub_tmp, kind;
+    // PLOC scratch
+    DevBuf<PlocState> pstate;
+    DevBuf<float4> qlo, qhi;
+    DevBuf<uint32_t> cl_a, cl_b, nn, psize, vals_dfs;
+    DevBuf<unsigned long long> pflags, ppos;
+    DevBuf<int2> pchildren;
+    DevBuf<int> pparent;
     const uint32_t n_int = n - 1, n_all = 2 * n - 1;
     RTB_CUDA(scratch.alloc(1));
     RTB_CUDA(plo.alloc(n)); RTB_CUDA(phi.alloc(n));
@@ -371,12 +574,31 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     RTB_CUDA(arrive.alloc(n_int)); RTB_CUDA(flags.alloc(n_int + 1)); RTB_CUDA(slot.alloc(n_int + 1));
     RTB_CUDA(children.alloc(n_int)); RTB_CUDA(range.alloc(n_int)); RTB_CUDA(parent.alloc(n_all));
     RTB_CUDA(flags4.alloc(n_int + 1)); RTB_CUDA(idx4.alloc(n_int + 1));
+    RTB_CUDA(kind.alloc(n_all));
+    static int builder = -1, ploc_r = 0, sah_leaves = 0;
+    if (builder < 0) {
+        const char* e = getenv("RTB_BUILDER");       // "karras" = plain radix tree, default PLOC
+        builder = (e && e[0] == 'k') ? 0 : 1;
+        const char* r = getenv("RTB_PLOC_R");
+        ploc_r = r ? std::min(PLOC_R_MAX, std::max(1, atoi(r))) : 16;
+        const char* l = getenv("RTB_SAH_LEAVES");
+        sah_leaves = l ? atoi(l) : 1;
+    }
+    const bool use_ploc = builder == 1 && n_int > 0 && !force_karras;
+    if (use_ploc) {
+        RTB_CUDA(pstate.alloc(1)); RTB_CUDA(qlo.alloc(n_all)); RTB_CUDA(qhi.alloc(n_all));
+        RTB_CUDA(cl_a.alloc(n)); RTB_CUDA(cl_b.alloc(n)); RTB_CUDA(nn.alloc(n)); RTB_CUDA(psize.alloc(n_all));
+        RTB_CUDA(vals_dfs.alloc(n)); RTB_CUDA(pflags.alloc(n)); RTB_CUDA(ppos.alloc(n));
+        RTB_CUDA(pchildren.alloc(n_int)); RTB_CUDA(pparent.alloc(n_all));
+    }
 
     size_t sort_bytes = 0, scan_bytes = 0;
     RTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n,
                                              0, 63, stream));
     RTB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags.p, slot.p, (int)(n_int + 1), stream));
-    size_t tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    size_t scan64_bytes = 0;
+    RTB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan64_bytes, pflags.p, ppos.p, (int)n, stream));
+    size_t tmp_bytes = std::max(sort_bytes, std::max(scan_bytes, scan64_bytes));
     RTB_CUDA(cub_tmp.alloc(tmp_bytes));
 
     const uint32_t B = 256;
@@ -389,18 +611,44 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
                                              0, 63, stream));
     launches += 8;  // cub's onesweep: histogram + ~7 digit passes for 63 bits (approximate)
     uint32_t total_split = 0;
-    if (n_int > 0) {
+    const uint32_t* leaf_vals = vals_sorted.p;     // primitive of every leaf, in leaf order
+    if (use_ploc) {
+        RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
+        k_ploc_init<<<cdiv(n, B), B, 0, stream>>>(n, vals_sorted.p, plo.p, phi.p, qlo.p, qhi.p, cl_a.p, psize.p, pparent.p,
+                                                  pstate.p); ++launches;
+        uint32_t m = n, base = 0;
+        uint32_t* cin = cl_a.p; uint32_t* cout = cl_b.p;
+        while (m > 1) {
+            k_ploc_nn<<<cdiv(m, PLOC_BLOCK), PLOC_BLOCK, 0, stream>>>(cin, pstate.p, qlo.p, qhi.p, ploc_r, nn.p);
+            k_ploc_flags<<<cdiv(m, B), B, 0, stream>>>(nn.p, pstate.p, pflags.p);
+            RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, pflags.p, ppos.p, (int)m, stream));
+            k_ploc_apply<<<cdiv(m, B), B, 0, stream>>>(n, cin, nn.p, ppos.p, pstate.p, cout, pchildren.p, pparent.p, qlo.p,
+                                                       qhi.p, psize.p, m, base);
+            launches += 4;
+            PlocState hs;
+            RTB_CUDA(cudaMemcpyAsync(&hs, pstate.p, sizeof hs, cudaMemcpyDeviceToHost, stream));
+            RTB_CUDA(cudaStreamSynchronize(stream));
+            if (hs.m >= m) { rtb_set_error("PLOC made no progress"); return RTB_ERR_CUDA; }
+            m = hs.m; base = hs.n_internal;
+            std::swap(cin, cout);
+        }
+        k_ploc_finish<<<cdiv(n_int, B), B, 0, stream>>>(n, pchildren.p, pparent.p, psize.p, vals_sorted.p, children.p,
+                                                        range.p, parent.p, vals_dfs.p); ++launches;
+        leaf_vals = vals_dfs.p;
+    } else if (n_int > 0) {
         RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
         k_hierarchy<<<cdiv(n_int, B), B, 0, stream>>>(keys_sorted.p, (int)n, children.p, range.p, parent.p); ++launches;
     } else {
         int minus1 = -1;
         RTB_CUDA(cudaMemcpyAsync(parent.p, &minus1, sizeof(int), cudaMemcpyHostToDevice, stream));
     }
-    k_refit<<<cdiv(n, B), B, 0, stream>>>(plo.p, phi.p, vals_sorted.p, (int)n, children.p, parent.p, blo.p, bhi.p,
+    k_refit<<<cdiv(n, B), B, 0, stream>>>(plo.p, phi.p, leaf_vals, (int)n, children.p, parent.p, blo.p, bhi.p,
                                           arrive.p, scratch.p); ++launches;
     k_leaf_depth<<<cdiv(n, B), B, 0, stream>>>((int)n, parent.p, scratch.p); ++launches;
+    k_node_kind<<<cdiv(n_all, B), B, 0, stream>>>((int)n, children.p, range.p, parent.p, blo.p, bhi.p, sah_leaves, kind.p);
+    ++launches;
     if (n_int > 0) {
-        k_split_flags<<<cdiv(n_int, B), B, 0, stream>>>(range.p, (int)n_int, flags.p); ++launches;
+        k_split_flags<<<cdiv(n_int, B), B, 0, stream>>>(kind.p, (int)n_int, flags.p); ++launches;
         RTB_CUDA(cudaMemsetAsync(flags.p + n_int, 0, sizeof(uint32_t), stream));
         RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, flags.p, slot.p, (int)(n_int + 1), stream));
         launches += 1;
@@ -409,14 +657,14 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     }
     out->n_nodes = 2 + 2 * total_split;
     RTB_CUDA(cudaMalloc(&out->d_nodes, sizeof(float4) * 2 * out->n_nodes));
-    k_emit_nodes<<<cdiv(n_all, B), B, 0, stream>>>((int)n, children.p, range.p, parent.p, blo.p, bhi.p, slot.p,
+    k_emit_nodes<<<cdiv(n_all, B), B, 0, stream>>>((int)n, children.p, range.p, parent.p, blo.p, bhi.p, slot.p, kind.p,
                                                    out->d_nodes, scratch.p); ++launches;
-    k_emit_tris<<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, vals_sorted.p, n, out->d_tri, out->d_shade,
+    k_emit_tris<<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, leaf_vals, n, out->d_tri, out->d_shade,
                                               out->d_prim_order); ++launches;
     // 4-wide collapse of the same tree (used by the wavefront renderer)
     uint32_t total4 = 1;
     if (n_int > 0) {
-        k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, range.p, parent.p, flags4.p, scratch.p); ++launches;
+        k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, kind.p, parent.p, flags4.p, scratch.p); ++launches;
         RTB_CUDA(cudaMemsetAsync(flags4.p + n_int, 0, sizeof(uint32_t), stream));
         RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, flags4.p, idx4.p, (int)(n_int + 1), stream));
         launches += 1;
@@ -426,7 +674,7 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
     out->n_nodes4 = total4;
     RTB_CUDA(cudaMalloc(&out->d_nodes4, sizeof(float4) * 8 * (size_t)total4));
     k_emit_nodes4<<<cdiv(n_int > 0 ? n_int : 1, B), B, 0, stream>>>((int)n, children.p, range.p, blo.p, bhi.p, flags4.p,
-                                                                  idx4.p, out->d_nodes4, scratch.p); ++launches;
+                                                                  idx4.p, kind.p, out->d_nodes4, scratch.p); ++launches;
     RTB_CUDA(cudaEventRecord(e1, stream));
     BuildScratch h;
     RTB_CUDA(cudaMemcpyAsync(&h, scratch.p, sizeof h, cudaMemcpyDeviceToHost, stream));

@@ -59,6 +59,7 @@ static std::vector<uint64_t> morton_sorted(std::vector<int>& order) {
 }
 
 static int collapse_leafmax = 4;
+static int lamb_below = 6320;
 
 // generic: given a binary topology over sorted leaves expressed as a recursive function, emit nodes with leaf collapse
 static Bvh2 build_lbvh() {
@@ -229,6 +230,7 @@ static int trace(const Bvh4& q, V o, V d, float& tbest, Cnt& c) {
 static float sah(const Bvh2& t) { double c = 0; float ra = t.n[t.root].box.area(); for (auto& n : t.n) c += n.box.area() / ra * (n.l < 0 ? 1.5 * n.count : 1.0); return (float)c; }
 
 int main(int argc, char** argv) {
+    if (argc > 2) lamb_below = atoi(argv[2]);
     FILE* f = fopen(argv[1], "rb"); std::vector<float> buf; float tmp[9];
     while (fread(tmp, 4, 9, f) == 9) { tris.push_back({{tmp[0], tmp[1], tmp[2]}, {tmp[3], tmp[4], tmp[5]}, {tmp[6], tmp[7], tmp[8]}}); }
     fclose(f);
@@ -237,9 +239,9 @@ int main(int argc, char** argv) {
     struct Cfg { const char* name; Bvh2 t; };
     std::vector<Cfg> cfgs;
     cfgs.push_back({"LBVH (GPU builder today)", build_lbvh()});
-    cfgs.push_back({"PLOC r=8", build_ploc(8, false)});
+
     cfgs.push_back({"PLOC r=16", build_ploc(16, false)});
-    cfgs.push_back({"PLOC r=32", build_ploc(32, false)});
+
     cfgs.push_back({"PLOC r=16 + SAH leaf split", build_ploc(16, true)});
     cfgs.push_back({"binned SAH top-down", build_sah()});
     // camera of main.rs at 4K, every 6th pixel
@@ -249,14 +251,14 @@ int main(int argc, char** argv) {
         Bvh4 q = collapse4(c.t);
         Cnt prim, bnc; std::mt19937 rng(1); std::uniform_real_distribution<float> U(-0.5f, 0.5f);
         int nleaf = 0, maxleaf = 0; for (auto& n : c.t.n) if (n.l < 0) { nleaf++; maxleaf = std::max(maxleaf, n.count); }
-        for (int r = 0; r < H; r += 6) for (int col = 0; col < W; col += 6) {
+        for (int r = 0; r < H; r += 12) for (int col = 0; col < W; col += 12) {
             V p = orig + vu * ((col + 0.5f) / W) + vv * ((r + 0.5f) / H); V d = unit(p - cam); float t;
             int h = trace(q, p, d, t, prim);
             int depth = 1;
             while (h >= 0 && depth < 5) {   // bounce: teapot (h < 6320) lambertian, disks mirror
                 V hp = p + d * t; const Tri& tr = tris[h]; V n = unit(cross(tr.b - tr.a, tr.c - tr.a)); if (dot(n, d) > 0) n = n * -1.f;
                 V nd;
-                if (h < 6320) { V rv = unit(V{U(rng), U(rng), U(rng)}); nd = unit(n + rv); } else nd = unit(d - n * (2.f * dot(d, n)));
+                if (h < lamb_below) { V rv = unit(V{U(rng), U(rng), U(rng)}); nd = unit(n + rv); } else nd = unit(d - n * (2.f * dot(d, n)));
                 p = hp + nd * 0.001f; d = nd; h = trace(q, p, d, t, bnc); depth++;
             }
         }
