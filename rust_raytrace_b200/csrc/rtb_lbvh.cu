@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <limits>
 #include <cstdlib>
 
 #include "rtb_internal.cuh"
@@ -458,8 +459,9 @@ __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const in
                 code[e] = idx4[c];
             }
         } else {
-            lo[0][e] = lo[1][e] = lo[2][e] = 1e30f;
-            hi[0][e] = hi[1][e] = hi[2][e] = -1e30f;
+            // empty slot: an all-NaN box.  fminf/fmaxf drop NaN operands, so the slab test ends with t_far = NaN and
+            // `t_near <= t_far` is false for every ray; an inverted box would NOT do (min/max re-order its planes)
+            lo[0][e] = lo[1][e] = lo[2][e] = hi[0][e] = hi[1][e] = hi[2][e] = __int_as_float(0x7fc00000);
             code[e] = 0u;
         }
     }
@@ -544,7 +546,12 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaStreamSynchronize(stream));
         out->n_nodes = 2;
         RTB_CUDA(cudaMalloc(&out->d_nodes4, sizeof(float4) * 8));
-        RTB_CUDA(cudaMemsetAsync(out->d_nodes4, 0, sizeof(float4) * 8, stream));   // all codes 0 = empty
+        // four empty slots: all-NaN boxes (the traversal recognises an empty slot by its box alone), codes 0
+        float4 h4[8];
+        const float qnan = std::numeric_limits<float>::quiet_NaN();
+        for (int a = 0; a < 6; ++a) h4[a] = make_float4(qnan, qnan, qnan, qnan);
+        h4[6] = h4[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+        RTB_CUDA(cudaMemcpyAsync(out->d_nodes4, h4, sizeof h4, cudaMemcpyHostToDevice, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
         out->n_nodes4 = 1;
         cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -29,7 +29,6 @@ using namespace rtbdev;
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr uint32_t INVALID_SLOT = 0xffffffffu;
 constexpr uint32_t LEAF_FLAG = 0x80000000u;
 constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent kernels
 constexpr int WF_OVF = 3 * (RTB_STACK / 2 + 1) + 2;   // worst-case BVH4 stack (tree height < RTB_STACK), thread-local overflow part
@@ -41,7 +40,8 @@ constexpr int WF_SMEM_STACK = 8;        // stack entries per thread kept in shar
 // pipeline with exact work fetch: (descend, refill) = (4,16) 2.82 ms, (4,20) 2.79, (4,24) 2.80, (4,28) 2.86,
 // (3,20) 2.79, (6,20) 2.87, (8,20) 2.90.
 constexpr uint32_t WF_DESCEND_MAX = 4;  // BVH4 node visits per lane per round before leaves are processed
-constexpr uint32_t WF_REFILL_MIN = 20;  // service (shade / refill) lanes once at least this many wait
+constexpr uint32_t WF_REFILL_MIN = 20;  // bounce kernel: service (shade / refill) lanes once at least this many wait
+constexpr uint32_t WF_REFILL_MIN_PRIMARY = 24;   // primary kernel: refill once at least this many lanes are done
 struct WfTune { uint32_t descend_max, refill_min; int smem_depth; };
 
 // slot -> pixel.  Slots enumerate 8x4 warp tiles inside the 8-row bands this launch renders.
@@ -158,7 +158,7 @@ __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, boo
             const float z0 = fmaf(LZ, s.iz, s.oz), z1 = fmaf(HZ, s.iz, s.oz);                           \
             const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));    \
             const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.0000005f;    \
-            key[c] = ((tn <= tf) && (tn <= s.tbest) && code[c] != 0u) ? tn : INF;                       \
+            key[c] = ((tn <= tf) && (tn <= s.tbest)) ? tn : INF;   /* an empty slot has a NaN box */     \
         }
         RTB_SLAB(0, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x)
         RTB_SLAB(1, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y)
@@ -548,24 +548,27 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     const int grid_t = sms * std::max(per_sm_t, 1), grid_b = sms * std::max(per_sm_b, 1);
     const uint32_t shade_blocks = std::min<uint32_t>((n_slots + 255u) / 256u, 148u * 16u);
     const uint32_t brute = (vw.flags & RTB_FLAG_BRUTE) ? 1u : 0u;
-    static uint32_t descend_max = 0, refill_min = 0;
+    static uint32_t descend_max = 0, refill_min = 0, refill_min_p = 0;
     if (descend_max == 0) {
         const char* e1 = getenv("RTB_WF_DESCEND");
         const char* e2 = getenv("RTB_WF_REFILL");
         descend_max = e1 ? (uint32_t)std::max(1, atoi(e1)) : WF_DESCEND_MAX;
         refill_min = e2 ? (uint32_t)std::min(32, std::max(1, atoi(e2))) : WF_REFILL_MIN;
+        const char* e3 = getenv("RTB_WF_REFILL_P");
+        refill_min_p = e3 ? (uint32_t)std::min(32, std::max(1, atoi(e3))) : WF_REFILL_MIN_PRIMARY;
     }
 
     const WfTune tune = {descend_max, refill_min, smem_depth};
+    const WfTune tune_p = {descend_max, refill_min_p, smem_depth};
     RTB_CUDA(cudaMemsetAsync(wc, 0, sizeof(WfCounters), stream));
     auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], stream); };
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
         mark(0);
         mark(1);
         if (stats)
-            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
+            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune_p, d_counters);
         else
-            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune, d_counters);
+            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune_p, d_counters);
         mark(2);
         k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
         mark(3);

@@ -172,8 +172,31 @@ static Bvh2 build_ploc(int R, bool sah_collapse) {
 // ---------------- BVH4 collapse + traversal ----------------
 struct N4 { Box b[4]; int code[4]; /* 0 empty, <0 leaf: -(idx2+1), >0: n4 index */ };
 struct Bvh4 { std::vector<N4> n; const Bvh2* src; };
+static bool greedy4 = false;
 static Bvh4 collapse4(const Bvh2& t) {
     Bvh4 q; q.src = &t;
+    if (greedy4) {
+        // expand the entry with the largest surface area until four slots are filled
+        std::function<int(int)> rec = [&](int c) -> int {
+            int id = (int)q.n.size(); q.n.emplace_back(); for (int k = 0; k < 4; ++k) q.n[id].code[k] = 0;
+            std::vector<int> ent;
+            if (t.n[c].l < 0) ent.push_back(c); else { ent.push_back(t.n[c].l); ent.push_back(t.n[c].r); }
+            while (ent.size() < 4) {
+                int bi = -1; float ba = -1;
+                for (size_t k = 0; k < ent.size(); ++k) if (t.n[ent[k]].l >= 0 && t.n[ent[k]].box.area() > ba) { ba = t.n[ent[k]].box.area(); bi = (int)k; }
+                if (bi < 0) break;
+                int e = ent[bi]; ent[bi] = t.n[e].l; ent.push_back(t.n[e].r);
+            }
+            for (size_t k = 0; k < ent.size(); ++k) {
+                q.n[id].b[k] = t.n[ent[k]].box;
+                if (t.n[ent[k]].l < 0) q.n[id].code[k] = -(ent[k] + 1);
+                else { int ci = rec(ent[k]); q.n[id].code[k] = ci; }
+            }
+            return id;
+        };
+        rec(t.root);
+        return q;
+    }
     std::function<int(int)> rec = [&](int c) -> int {
         int id = (int)q.n.size(); q.n.emplace_back(); for (int k = 0; k < 4; ++k) q.n[id].code[k] = 0;
         std::vector<int> ent;
@@ -247,7 +270,10 @@ int main(int argc, char** argv) {
     // camera of main.rs at 4K, every 6th pixel
     V orig{2.28125f, -0.5f, 0.f}, cam{2.f, 0.f, -0.5f}, vu{0, 1, 0}, vv{-0.5625f, 0, 0};
     int W = 3840, H = 2160;
+    for (int pass = 0; pass < 2; ++pass)
     for (auto& c : cfgs) {
+        greedy4 = pass == 1;
+        if (greedy4) printf("[greedy BVH4 collapse] ");
         Bvh4 q = collapse4(c.t);
         Cnt prim, bnc; std::mt19937 rng(1); std::uniform_real_distribution<float> U(-0.5f, 0.5f);
         int nleaf = 0, maxleaf = 0; for (auto& n : c.t.n) if (n.l < 0) { nleaf++; maxleaf = std::max(maxleaf, n.count); }
