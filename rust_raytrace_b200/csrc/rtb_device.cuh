@@ -87,22 +87,25 @@ __device__ __forceinline__ void gen_primary(const ViewDev& vw, uint32_t row, uin
 // Returns true and t when the reference would return Some(..).  `has`/`best` allow skipping work
 // that cannot change the running minimum (t > best can never win under strict-< / lowest-index).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ bool tri_test(const float4* __restrict__ q, V3 o, V3 d, bool has, float best, float* t_out) {
-    const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
+__device__ __forceinline__ bool tri_test_pre(const float4* __restrict__ q, float4 q0, float4 q1, V3 o, V3 d, bool has,
+                                             float best, float* t_out) {
     const V3 n = mk(q0.x, q0.y, q0.z), c = mk(q1.x, q1.y, q1.z);
     const float t = __fdiv_rn(vdot(n, vsub(c, o)), vdot(n, d));
     if (t < 0.0f) return false;
     if (has && t > best) return false;
     const V3 ip = vsub(vadd(vmul(d, t), o), c);
     if (vdot(ip, ip) > q0.w) return false;
-    const float4 q2 = __ldg(q + 2);
+    // the three edge records together: one latency instead of up to three (ncu r1_v5: these dependent loads held
+    // 11 % of the bounce kernel's stall samples at ~4 active lanes)
+    const float4 q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
     if (vdot(ip, mk(q2.x, q2.y, q2.z)) > q2.w) return false;
-    const float4 q3 = __ldg(q + 3);
     if (vdot(ip, mk(q3.x, q3.y, q3.z)) > q3.w) return false;
-    const float4 q4 = __ldg(q + 4);
     if (vdot(ip, mk(q4.x, q4.y, q4.z)) > q4.w) return false;
     *t_out = t;
     return true;
+}
+__device__ __forceinline__ bool tri_test(const float4* __restrict__ q, V3 o, V3 d, bool has, float best, float* t_out) {
+    return tri_test_pre(q, __ldg(q + 0), __ldg(q + 1), o, d, has, best, t_out);
 }
 
 struct Hit {

@@ -40,7 +40,9 @@ struct SceneDev {
 
 #define RTB_TRI_F4 5
 #define RTB_SHADE_F4 2
+#ifndef RTB_LEAF_MAX
 #define RTB_LEAF_MAX 4
+#endif
 #define RTB_STACK 64
 #define RTB_MAX_CHUNKS 16
 #define RTB_MAX_LANES 4

@@ -33,6 +33,9 @@ constexpr uint32_t LEAF_FLAG = 0x80000000u;
 constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent kernels
 constexpr int WF_OVF = 3 * (RTB_STACK / 2 + 1) + 2;   // worst-case BVH4 stack (tree height < RTB_STACK), thread-local overflow part
 constexpr int WF_SMEM_STACK = 8;        // stack entries per thread kept in shared memory
+#ifndef WF_TRACE_MIN_BLOCKS
+#define WF_TRACE_MIN_BLOCKS 4
+#endif
 #ifndef WF_BOUNCE_MIN_BLOCKS
 #define WF_BOUNCE_MIN_BLOCKS 8          // 64 registers: 32 warps/SM instead of 24 at the natural 80
 #endif
@@ -186,12 +189,16 @@ __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, boo
     }
     if (trav && (s.cur & LEAF_FLAG)) {
         const uint32_t first = (s.cur & ~LEAF_FLAG) >> 3, cnt = s.cur & 7u;
-        for (uint32_t k = first; k < first + cnt; ++k) {
+        // software pipeline: the first 32 bytes of triangle k+1 are in flight while triangle k is tested
+        const float4* q = sc.tri + (size_t)RTB_TRI_F4 * first;
+        float4 a0 = __ldg(q), a1 = __ldg(q + 1);
+        for (uint32_t k = first; k < first + cnt; ++k, q += RTB_TRI_F4) {
             float t;
             if (STATS) ++n_tri;
-            const float4* q = sc.tri + (size_t)RTB_TRI_F4 * k;
-            if (tri_test(q, s.o, s.d, s.h.slot >= 0, s.h.t, &t)) {
-                const uint32_t orig = __float_as_uint(__ldg(q + 1).w);
+            const float4 c0 = a0, c1 = a1;
+            if (k + 1u < first + cnt) { a0 = __ldg(q + RTB_TRI_F4); a1 = __ldg(q + RTB_TRI_F4 + 1); }
+            if (tri_test_pre(q, c0, c1, s.o, s.d, s.h.slot >= 0, s.h.t, &t)) {
+                const uint32_t orig = __float_as_uint(c1.w);
                 if (s.h.slot < 0 || t < s.h.t || (t == s.h.t && orig < s.h.orig)) {
                     s.h.t = t; s.h.slot = (int)k; s.h.orig = orig;
                     if (t < s.tbest) s.tbest = t;      // a NaN t never tightens the bound
@@ -238,7 +245,7 @@ struct WorkFetch {
 // stage 1: closest hit of the primary rays, persistent threads with per-lane refill
 // ---------------------------------------------------------------------------
 template <bool STATS>
-__global__ void __launch_bounds__(WF_BLOCK, 4)
+__global__ void __launch_bounds__(WF_BLOCK, WF_TRACE_MIN_BLOCKS)
 k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
            float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, const WfTune tune,
            TraceCounters* __restrict__ counters) {
