@@ -210,20 +210,22 @@ __global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nn(const uint32_t* __restri
 }
 
 // flags for the compaction scan: low word = "stays in the array", high word = "creates a node"
-__global__ void k_ploc_flags(const uint32_t* __restrict__ nn, const PlocState* st, unsigned long long* __restrict__ flags) {
+__global__ void k_ploc_flags(const uint32_t* __restrict__ nn, const PlocState* st, unsigned long long* __restrict__ flags,
+                             uint32_t m_upper) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t m = st->m;
-    if (i >= m) return;
+    if (i >= m) { if (i < m_upper) flags[i] = 0ull; return; }   // the host's bound on m may be a few rounds old
     const uint32_t j = nn[i];
     const bool mutual = (j < m) && nn[j] == i;
     flags[i] = mutual ? (i < j ? ((1ull << 32) | 1ull) : 0ull) : 1ull;
 }
 
 __global__ void k_ploc_apply(uint32_t n, const uint32_t* __restrict__ cin, const uint32_t* __restrict__ nn,
-                             const unsigned long long* __restrict__ pos, PlocState* st, uint32_t* __restrict__ cout,
-                             int2* __restrict__ pchildren, int* __restrict__ parent, float4* __restrict__ lo,
-                             float4* __restrict__ hi, uint32_t* __restrict__ size, uint32_t m, uint32_t base) {
+                             const unsigned long long* __restrict__ pos, const PlocState* st_in, PlocState* st_out,
+                             uint32_t* __restrict__ cout, int2* __restrict__ pchildren, int* __restrict__ parent,
+                             float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* __restrict__ size) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m = st_in->m, base = st_in->n_internal;
     if (i >= m) return;
     const uint32_t j = nn[i];
     const bool mutual = (j < m) && nn[j] == i;
@@ -248,7 +250,91 @@ __global__ void k_ploc_apply(uint32_t n, const uint32_t* __restrict__ cin, const
     } else {
         cout[out] = cin[i];
     }
-    if (i == m - 1) { st->m = out + keeps; st->n_internal = base + created + creates; }
+    if (i == m - 1) { st_out->m = out + keeps; st_out->n_internal = base + created + creates; }
+}
+
+
+// The last rounds (<= PLOC_TAIL clusters) in ONE block: nearest neighbours, mutual-pair merge and compaction loop in
+// shared memory with __syncthreads between the phases, instead of four launches and a host round trip per round —
+// for the 6,720-triangle teapot scene that is 15 of the ~19 rounds.
+constexpr int PLOC_TAIL = 1024;
+__global__ void __launch_bounds__(PLOC_TAIL) k_ploc_tail(uint32_t n, const uint32_t* __restrict__ cin, const PlocState* st_in,
+                                                        PlocState* st_out, int R, int2* __restrict__ pchildren,
+                                                        int* __restrict__ parent, float4* __restrict__ lo,
+                                                        float4* __restrict__ hi, uint32_t* __restrict__ size) {
+    __shared__ uint32_t C[2][PLOC_TAIL];
+    __shared__ uint32_t nn[PLOC_TAIL];
+    __shared__ uint32_t wsum_keep[32], wsum_make[32];
+    __shared__ uint32_t tot_keep, tot_make;
+    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    int m = (int)st_in->m;
+    uint32_t base = st_in->n_internal;
+    if (i < m) C[0][i] = cin[i];
+    int cur = 0;
+    __syncthreads();
+    while (m > 1) {
+        // nearest neighbour
+        uint32_t bj = 0xffffffffu;
+        if (i < m) {
+            const uint32_t ci = C[cur][i];
+            const float4 al = lo[ci], ah = hi[ci];
+            float best = FLT_MAX;
+            for (int j = max(0, i - R); j <= min(m - 1, i + R); ++j) {
+                if (j == i) continue;
+                const uint32_t cj = C[cur][j];
+                const float a = union_area(al, ah, lo[cj], hi[cj]);
+                if (a < best) { best = a; bj = (uint32_t)j; }
+            }
+            nn[i] = bj;
+        }
+        __syncthreads();
+        const bool mutual = (i < m) && bj < (uint32_t)m && nn[bj] == (uint32_t)i;
+        const uint32_t make = (mutual && (uint32_t)i < bj) ? 1u : 0u;
+        const uint32_t keep = (i < m) ? ((mutual && !make) ? 0u : 1u) : 0u;
+        // block-wide exclusive scan of (keep, make)
+        uint32_t sk = keep, sm = make;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t uk = __shfl_up_sync(0xffffffffu, sk, off), um = __shfl_up_sync(0xffffffffu, sm, off);
+            if (lane >= off) { sk += uk; sm += um; }
+        }
+        if (lane == 31) { wsum_keep[warp] = sk; wsum_make[warp] = sm; }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t a = wsum_keep[lane], b = wsum_make[lane];
+            const uint32_t a0 = a, b0 = b;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t ua = __shfl_up_sync(0xffffffffu, a, off), ub = __shfl_up_sync(0xffffffffu, b, off);
+                if (lane >= off) { a += ua; b += ub; }
+            }
+            wsum_keep[lane] = a - a0; wsum_make[lane] = b - b0;       // exclusive warp offsets
+            if (lane == 31) { tot_keep = a; tot_make = b; }
+        }
+        __syncthreads();
+        const uint32_t out = wsum_keep[warp] + sk - keep, created = wsum_make[warp] + sm - make;
+        if (i < m) {
+            if (make) {
+                const uint32_t a = C[cur][i], b = C[cur][bj];
+                const uint32_t id = n + base + created;
+                pchildren[id - n] = make_int2((int)a, (int)b);
+                parent[a] = (int)id; parent[b] = (int)id; parent[id] = -1;
+                const float4 al = lo[a], ah = hi[a], bl = lo[b], bh = hi[b];
+                lo[id] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
+                hi[id] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+                size[id] = size[a] + size[b];
+                C[cur ^ 1][out] = id;
+            } else if (keep) {
+                C[cur ^ 1][out] = C[cur][i];
+            }
+        }
+        __syncthreads();
+        m = (int)tot_keep;
+        base += tot_make;
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (i == 0) { st_out->m = 1u; st_out->n_internal = base; }
 }
 
 // PLOC ids -> the builder's node convention + DFS primitive order.  One thread per internal PLOC node.
@@ -593,7 +679,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     }
     const bool use_ploc = builder == 1 && n_int > 0 && !force_karras;
     if (use_ploc) {
-        RTB_CUDA(pstate.alloc(1)); RTB_CUDA(qlo.alloc(n_all)); RTB_CUDA(qhi.alloc(n_all));
+        RTB_CUDA(pstate.alloc(2)); RTB_CUDA(qlo.alloc(n_all)); RTB_CUDA(qhi.alloc(n_all));
         RTB_CUDA(cl_a.alloc(n)); RTB_CUDA(cl_b.alloc(n)); RTB_CUDA(nn.alloc(n)); RTB_CUDA(psize.alloc(n_all));
         RTB_CUDA(vals_dfs.alloc(n)); RTB_CUDA(pflags.alloc(n)); RTB_CUDA(ppos.alloc(n));
         RTB_CUDA(pchildren.alloc(n_int)); RTB_CUDA(pparent.alloc(n_all));
@@ -623,21 +709,34 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
         k_ploc_init<<<cdiv(n, B), B, 0, stream>>>(n, vals_sorted.p, plo.p, phi.p, qlo.p, qhi.p, cl_a.p, psize.p, pparent.p,
                                                   pstate.p); ++launches;
-        uint32_t m = n, base = 0;
+        // Rounds run in groups of PLOC_GROUP between host reads of the cluster count: the grids of a group are sized for
+        // the count at its start (a stale upper bound, the kernels read the true count on the device), the two
+        // PlocState slots alternate as input and output.
+        constexpr int PLOC_GROUP = 3;
+        uint32_t m_upper = n;
         uint32_t* cin = cl_a.p; uint32_t* cout = cl_b.p;
-        while (m > 1) {
-            k_ploc_nn<<<cdiv(m, PLOC_BLOCK), PLOC_BLOCK, 0, stream>>>(cin, pstate.p, qlo.p, qhi.p, ploc_r, nn.p);
-            k_ploc_flags<<<cdiv(m, B), B, 0, stream>>>(nn.p, pstate.p, pflags.p);
-            RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, pflags.p, ppos.p, (int)m, stream));
-            k_ploc_apply<<<cdiv(m, B), B, 0, stream>>>(n, cin, nn.p, ppos.p, pstate.p, cout, pchildren.p, pparent.p, qlo.p,
-                                                       qhi.p, psize.p, m, base);
-            launches += 4;
+        int it = 0;
+        while (m_upper > (uint32_t)PLOC_TAIL) {
+            for (int k = 0; k < PLOC_GROUP; ++k, ++it) {
+                const PlocState* si = pstate.p + (it & 1);
+                PlocState* so = pstate.p + ((it + 1) & 1);
+                k_ploc_nn<<<cdiv(m_upper, PLOC_BLOCK), PLOC_BLOCK, 0, stream>>>(cin, si, qlo.p, qhi.p, ploc_r, nn.p);
+                k_ploc_flags<<<cdiv(m_upper, B), B, 0, stream>>>(nn.p, si, pflags.p, m_upper);
+                RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, pflags.p, ppos.p, (int)m_upper, stream));
+                k_ploc_apply<<<cdiv(m_upper, B), B, 0, stream>>>(n, cin, nn.p, ppos.p, si, so, cout, pchildren.p, pparent.p,
+                                                             qlo.p, qhi.p, psize.p);
+                launches += 4;
+                std::swap(cin, cout);
+            }
             PlocState hs;
-            RTB_CUDA(cudaMemcpyAsync(&hs, pstate.p, sizeof hs, cudaMemcpyDeviceToHost, stream));
+            RTB_CUDA(cudaMemcpyAsync(&hs, pstate.p + (it & 1), sizeof hs, cudaMemcpyDeviceToHost, stream));
             RTB_CUDA(cudaStreamSynchronize(stream));
-            if (hs.m >= m) { rtb_set_error("PLOC made no progress"); return RTB_ERR_CUDA; }
-            m = hs.m; base = hs.n_internal;
-            std::swap(cin, cout);
+            if (hs.m >= m_upper) { rtb_set_error("PLOC made no progress"); return RTB_ERR_CUDA; }
+            m_upper = hs.m;
+        }
+        if (m_upper > 1) {
+            k_ploc_tail<<<1, PLOC_TAIL, 0, stream>>>(n, cin, pstate.p + (it & 1), pstate.p + ((it + 1) & 1), ploc_r, pchildren.p,
+                                                     pparent.p, qlo.p, qhi.p, psize.p); ++launches;
         }
         k_ploc_finish<<<cdiv(n_int, B), B, 0, stream>>>(n, pchildren.p, pparent.p, psize.p, vals_sorted.p, children.p,
                                                         range.p, parent.p, vals_dfs.p); ++launches;
