@@ -46,12 +46,14 @@ struct SceneDev {
 #define RTB_STACK 64
 #define RTB_MAX_CHUNKS 16
 #define RTB_MAX_LANES 4
-// Measured on B200 (4K teapot frame, ms per frame; pieces/lanes), raygen + trace + shade + bounce pipeline:
-// device-resident output 1/1 3.12, 2/2 3.12, 4/4 3.39, 8/4 3.46; host output incl. the 133 MB D2H (2.34 ms alone)
-// 1/1 5.56, 2/2 4.81, 4/4 4.14, 6/3 4.00, 8/4 4.00.
+// rtb_render (host output) renders the frame's bands in pieces on a few streams so that the D2H copy of a finished
+// piece (own copy stream) overlaps the kernels of the next ones.  Measured on B200, 4K teapot frame, ms per call incl.
+// the 133 MB D2H (2.34 ms alone; one full-frame render 2.47 ms): pieces/lanes 4/1 3.70, 4/2 3.62, 8/1 4.00, 8/2 3.47,
+// 8/4 4.07, 12/3 3.81, 16/2 3.95, 16/4 4.32.  Every piece pays its own launches and kernel tails (8 pieces on one
+// stream: 3.65 ms of device time), so more pieces is not better.
 #define RTB_DEFAULT_PIECES 8          /* rtb_render: more pieces = earlier D2H overlap */
 #define RTB_DEFAULT_PIECES_DEVICE 1   /* rtb_render_device: no copies to overlap */
-#define RTB_DEFAULT_LANES 4
+#define RTB_DEFAULT_LANES 2
 
 // Image tiling: one CTA = 128 threads = 16 x 8 pixels; one warp = 8 x 4 pixels.
 #define RTB_TILE_W 16
