@@ -185,6 +185,10 @@ int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out);
  * Host-only; needs no GPU. */
 int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t* rows_out, uint32_t cap);
 
+/* Device self-test of the BVH builder's hand-written radix sort (stable, 64-bit keys, 32-bit values) and exclusive
+ * scans against the host on n pseudo-random pairs with key_bits significant key bits. */
+int rtb_selftest_sort(uint32_t n, int key_bits, uint64_t seed);
+
 /* Pin / unpin a caller-owned host buffer (cudaHostRegister) so D2H runs at PCIe speed. */
 int rtb_host_register(void* ptr, size_t bytes);
 int rtb_host_unregister(void* ptr);

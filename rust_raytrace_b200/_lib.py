@@ -98,7 +98,7 @@ class RtbSurface(C.Structure):
 RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render", "rtb_render_device", "rtb_render_progressive",
-    "rtb_quantize_rgb8", "rtb_scale_device", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
+    "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
 ]
 RTBH_SYMBOLS = [
     "rtbh_make_color", "rtbh_unit", "rtbh_to_radians", "rtbh_make_triangle", "rtbh_make_dummy_triangle",
@@ -143,6 +143,7 @@ def lib():
     L.rtb_render_progressive.argtypes = [vp, C.POINTER(RtbView), vp, C.POINTER(RtbStats)]
     L.rtb_quantize_rgb8.argtypes = [vp, C.c_uint64, vp]
     L.rtb_scale_device.argtypes = [vp, C.c_uint64, u32, C.c_int, vp]
+    L.rtb_selftest_sort.argtypes = [u32, C.c_int, C.c_uint64]
     L.rtb_partition_rows.argtypes = [u32, u32, u32, vp, u32]
     L.rtb_host_register.argtypes = [vp, C.c_size_t]
     L.rtb_host_unregister.argtypes = [vp]

@@ -624,6 +624,14 @@ int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out) {
     return RTB_OK;
 }
 
+int rtb_selftest_sort(uint32_t n, int key_bits, uint64_t seed) {
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    if (key_bits < 1 || key_bits > 64) return fail(RTB_ERR_INVALID, "key_bits must be in [1, 64]");
+    RTB_CUDA(cudaSetDevice(g_devices[0]));
+    return rtb_sort_selftest(n, key_bits, seed);
+}
+
 int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t* rows_out, uint32_t cap) {
     if (world == 0 || rank >= world) return fail(RTB_ERR_INVALID, "bad rank/world");
     uint32_t n = 0;

@@ -149,6 +149,9 @@ struct BuildResult {
 int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n_prims, cudaStream_t stream,
                    BuildResult* out);
 
+// Self-test of the hand-written radix sort / scan (rtb_sort.cuh) against the host.
+int rtb_sort_selftest(uint32_t n, int key_bits, uint64_t seed);
+
 // ---- implemented in rtb_trace.cu ----------------------------------------------
 // Launches the trace kernel for the tile rows owned by (tile_rank, tile_world).
 int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint32_t* d_prim, float* d_t,

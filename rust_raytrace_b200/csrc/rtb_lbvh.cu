@@ -5,21 +5,22 @@
 // Pipeline (all on one stream, no host round trip until the final info read-back):
 //   k_prim_bounds   per-primitive AABB from `corners`, scene AABB by atomic min/max
 //   k_morton        63-bit Morton code of the AABB centre
-//   radix sort      (key = morton, value = primitive)            [cub::DeviceRadixSort — interim]
+//   radix sort      (key = morton, value = primitive): 8 stable LSD passes of 8 bits, rtb_sort.cuh
 //   k_hierarchy     Karras 2012 radix-tree: children, parent, covered range per internal node
 //   k_refit         bottom-up AABB union with one atomic arrival counter per internal node
-//   exclusive scan  over "this internal node covers > RTB_LEAF_MAX primitives" [cub::DeviceScan — interim]
+//   exclusive scan  over "this internal node stays internal" (rtb_sort.cuh)
 //   k_emit_nodes    collapse small subtrees into leaves, write 32-byte nodes with adjacent sibling pairs
 //   k_emit_tris     gather the 19 intersect floats + shading record of each primitive into leaf order
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cfloat>
 #include <limits>
+#include <string>
+#include <vector>
 #include <cstdlib>
 
 #include "rtb_internal.cuh"
+#include "rtb_sort.cuh"
 
 namespace {
 
@@ -650,7 +651,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     DevBuf<uint32_t> vals, vals_sorted, arrive, flags, slot, flags4, idx4;
     DevBuf<int2> children, range;
     DevBuf<int> parent;
-    DevBuf<uint8_t> cub_tmp, kind;
+    DevBuf<uint8_t> sort_tmp, kind;
     // PLOC scratch
     DevBuf<PlocState> pstate;
     DevBuf<float4> qlo, qhi;
@@ -685,14 +686,9 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(pchildren.alloc(n_int)); RTB_CUDA(pparent.alloc(n_all));
     }
 
-    size_t sort_bytes = 0, scan_bytes = 0;
-    RTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n,
-                                             0, 63, stream));
-    RTB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags.p, slot.p, (int)(n_int + 1), stream));
-    size_t scan64_bytes = 0;
-    RTB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan64_bytes, pflags.p, ppos.p, (int)n, stream));
-    size_t tmp_bytes = std::max(sort_bytes, std::max(scan_bytes, scan64_bytes));
-    RTB_CUDA(cub_tmp.alloc(tmp_bytes));
+    const size_t tmp_bytes = std::max(rtbsort::sort_tmp_bytes(n), std::max(rtbsort::scan_tmp_bytes<uint32_t>(n_int + 1),
+                                                                          rtbsort::scan_tmp_bytes<unsigned long long>(n)));
+    RTB_CUDA(sort_tmp.alloc(tmp_bytes));
 
     const uint32_t B = 256;
     uint32_t launches = 0;
@@ -700,9 +696,12 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     k_init_scratch<<<1, 32, 0, stream>>>(scratch.p); ++launches;
     k_prim_bounds<<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, n, plo.p, phi.p, scratch.p); ++launches;
     k_morton<<<cdiv(n, B), B, 0, stream>>>(plo.p, phi.p, n, scratch.p, keys.p, vals.p); ++launches;
-    RTB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n,
-                                             0, 63, stream));
-    launches += 8;  // cub's onesweep: histogram + ~7 digit passes for 63 bits (approximate)
+    {
+        bool in_b = false;
+        launches += (uint32_t)rtbsort::radix_sort_pairs((unsigned long long*)keys.p, (unsigned long long*)keys_sorted.p, vals.p,
+                                                        vals_sorted.p, n, 63, sort_tmp.p, stream, &in_b);
+        if (!in_b) { std::swap(keys.p, keys_sorted.p); std::swap(vals.p, vals_sorted.p); }   // result -> *_sorted
+    }
     uint32_t total_split = 0;
     const uint32_t* leaf_vals = vals_sorted.p;     // primitive of every leaf, in leaf order
     if (use_ploc) {
@@ -722,10 +721,10 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
                 PlocState* so = pstate.p + ((it + 1) & 1);
                 k_ploc_nn<<<cdiv(m_upper, PLOC_BLOCK), PLOC_BLOCK, 0, stream>>>(cin, si, qlo.p, qhi.p, ploc_r, nn.p);
                 k_ploc_flags<<<cdiv(m_upper, B), B, 0, stream>>>(nn.p, si, pflags.p, m_upper);
-                RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, pflags.p, ppos.p, (int)m_upper, stream));
+                rtbsort::exclusive_sum<unsigned long long>(pflags.p, ppos.p, m_upper, sort_tmp.p, stream);
                 k_ploc_apply<<<cdiv(m_upper, B), B, 0, stream>>>(n, cin, nn.p, ppos.p, si, so, cout, pchildren.p, pparent.p,
                                                              qlo.p, qhi.p, psize.p);
-                launches += 4;
+                launches += 6;
                 std::swap(cin, cout);
             }
             PlocState hs;
@@ -756,8 +755,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     if (n_int > 0) {
         k_split_flags<<<cdiv(n_int, B), B, 0, stream>>>(kind.p, (int)n_int, flags.p); ++launches;
         RTB_CUDA(cudaMemsetAsync(flags.p + n_int, 0, sizeof(uint32_t), stream));
-        RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, flags.p, slot.p, (int)(n_int + 1), stream));
-        launches += 1;
+        launches += (uint32_t)rtbsort::exclusive_sum<uint32_t>(flags.p, slot.p, n_int + 1, sort_tmp.p, stream);
         RTB_CUDA(cudaMemcpyAsync(&total_split, slot.p + n_int, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -772,8 +770,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     if (n_int > 0) {
         k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, kind.p, parent.p, flags4.p, scratch.p); ++launches;
         RTB_CUDA(cudaMemsetAsync(flags4.p + n_int, 0, sizeof(uint32_t), stream));
-        RTB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp_bytes, flags4.p, idx4.p, (int)(n_int + 1), stream));
-        launches += 1;
+        launches += (uint32_t)rtbsort::exclusive_sum<uint32_t>(flags4.p, idx4.p, n_int + 1, sort_tmp.p, stream);
         RTB_CUDA(cudaMemcpyAsync(&total4, idx4.p + n_int, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -801,5 +798,59 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
                       std::to_string(RTB_STACK) + ")");
         return RTB_ERR_INVALID;
     }
+    return RTB_OK;
+}
+
+// Self-test of the builder's sort and scan against the host (std::stable_sort / a running sum): n random pairs with
+// `key_bits` significant key bits (few bits = many equal keys = the stability check).  RTB_OK or RTB_ERR_INVALID.
+int rtb_sort_selftest(uint32_t n, int key_bits, uint64_t seed) {
+    std::vector<unsigned long long> keys(n);
+    std::vector<uint32_t> vals(n);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    const unsigned long long mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
+    for (uint32_t i = 0; i < n; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        keys[i] = x & mask; vals[i] = i;
+    }
+    DevBuf<unsigned long long> ka, kb, s64;
+    DevBuf<uint32_t> va, vb, s32;
+    DevBuf<uint8_t> tmp;
+    RTB_CUDA(ka.alloc(n)); RTB_CUDA(kb.alloc(n)); RTB_CUDA(va.alloc(n)); RTB_CUDA(vb.alloc(n));
+    RTB_CUDA(s64.alloc(n)); RTB_CUDA(s32.alloc(n));
+    RTB_CUDA(tmp.alloc(std::max(rtbsort::sort_tmp_bytes(n), rtbsort::scan_tmp_bytes<unsigned long long>(n))));
+    RTB_CUDA(cudaMemcpy(ka.p, keys.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(va.p, vals.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    bool in_b = false;
+    rtbsort::radix_sort_pairs(ka.p, kb.p, va.p, vb.p, n, key_bits, tmp.p, 0, &in_b);
+    std::vector<unsigned long long> gk(n);
+    std::vector<uint32_t> gv(n);
+    RTB_CUDA(cudaMemcpy(gk.data(), in_b ? kb.p : ka.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+    RTB_CUDA(cudaMemcpy(gv.data(), in_b ? vb.p : va.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    for (uint32_t i = 0; i < n; ++i)
+        if (gv[i] != order[i] || gk[i] != keys[order[i]]) {
+            rtb_set_error("radix sort mismatch at " + std::to_string(i));
+            return RTB_ERR_INVALID;
+        }
+    // scans: 64-bit over the keys' low 20 bits, 32-bit over the values' low 4 bits
+    std::vector<unsigned long long> h64(n);
+    std::vector<uint32_t> h32(n);
+    for (uint32_t i = 0; i < n; ++i) { h64[i] = keys[i] & 0xfffffull; h32[i] = vals[i] & 15u; }
+    RTB_CUDA(cudaMemcpy(s64.p, h64.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(s32.p, h32.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    rtbsort::exclusive_sum<unsigned long long>(s64.p, s64.p, n, tmp.p, 0);
+    std::vector<unsigned long long> g64(n);
+    RTB_CUDA(cudaMemcpy(g64.data(), s64.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+    rtbsort::exclusive_sum<uint32_t>(s32.p, s32.p, n, tmp.p, 0);
+    std::vector<uint32_t> g32(n);
+    RTB_CUDA(cudaMemcpy(g32.data(), s32.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    unsigned long long r64 = 0; uint32_t r32 = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (g64[i] != r64 || g32[i] != r32) { rtb_set_error("exclusive sum mismatch at " + std::to_string(i)); return RTB_ERR_INVALID; }
+        r64 += h64[i]; r32 += h32[i];
+    }
+    RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }

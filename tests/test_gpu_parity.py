@@ -239,6 +239,13 @@ def test_stats_variant_and_bvh_shape(R, scenes):
     assert st.node_tests > st.rays and st.tri_tests > 0 and st.node_tests / st.rays < 200
 
 
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 3), (4096, 64), (4097, 63), (100000, 5), (1 << 20, 63), (3000001, 40)])
+def test_builder_sort_and_scan(R, n, bits):
+    """The LBVH builder's hand-written stable radix sort and exclusive scans against std::stable_sort / a host sum."""
+    from rust_raytrace_b200 import _lib
+    _lib.check(_lib.lib().rtb_selftest_sort(n, bits, 1234 + n), "rtb_selftest_sort")
+
+
 def test_quantiser_on_gpu(R, O):
     px = np.random.RandomState(0).uniform(-0.2, 1.2, (1000, 4)).astype(np.float32)
     px[0, :3] = [np.nan, 1.0, 0.0]
