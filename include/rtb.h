@@ -91,8 +91,10 @@ enum {
                                  build_trivial_bounding_box, raytrace.rs:847-856)                  */
     RTB_FLAG_MEGAKERNEL = 8u, /* A/B: the one-kernel-per-frame renderer (rtb_trace.cu) instead of the
                                  default wavefront pipeline (rtb_wavefront.cu); same results        */
-    RTB_FLAG_TIMING   = 16u   /* rtb_render_device only: bracket every pipeline stage with CUDA events on the
+    RTB_FLAG_TIMING   = 16u,  /* rtb_render_device only: bracket every pipeline stage with CUDA events on the
                                  launching stream and report RtbStats.ms_stage (one piece, one lane)  */
+    RTB_FLAG_POOL     = 32u   /* A/B: bounce kernel variant with a shared-memory pool of 64 rays per warp (fuller
+                                 warps, more state traffic; rtb_wavefront.cu); same results              */
 };
 
 /* Pipeline stages of the wavefront renderer, indices into RtbStats.ms_stage. */

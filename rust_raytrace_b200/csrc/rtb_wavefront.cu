@@ -45,7 +45,7 @@ constexpr int WF_SMEM_STACK = 8;        // stack entries per thread kept in shar
 constexpr uint32_t WF_DESCEND_MAX = 4;  // BVH4 node visits per lane per round before leaves are processed
 constexpr uint32_t WF_REFILL_MIN = 20;  // bounce kernel: service (shade / refill) lanes once at least this many wait
 constexpr uint32_t WF_REFILL_MIN_PRIMARY = 24;   // primary kernel: refill once at least this many lanes are done
-struct WfTune { uint32_t descend_max, refill_min; int smem_depth; };
+struct WfTune { uint32_t descend_max, refill_min; int smem_depth; uint32_t pool_node_min; };
 
 // slot -> pixel.  Slots enumerate 8x4 warp tiles inside the 8-row bands this launch renders.
 struct Pixel { uint32_t row, col, out_idx; bool inside; };
@@ -484,6 +484,277 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
     }
 }
 
+// ---------------------------------------------------------------------------
+// stage 3, pool variant: the same function as k_wf_bounce, organised for lane utilisation.
+//
+// k_wf_bounce keeps one ray per lane in registers, so an instruction of the traversal loop only serves the lanes
+// whose ray happens to need that step: 14.5 of 32 lanes in a node visit, 8-11 in a triangle test, ~20 in shading
+// (ncu r1_v5).  Here a warp owns a POOL of 64 rays whose state lives in shared memory; before every step the warp
+// counts how many pooled rays want a node visit / a leaf / shading / a refill, picks the kind with the most
+// candidates and deals (up to) 32 of them out to its lanes (ballot + popc ranks), so each step runs closer to full
+// width.  The price is the state traffic: a node step loads 9 and stores 2-5 words of ray state per lane.
+//
+// Measured on B200 (ncu, 4K teapot frame): active lanes per instruction 12.8 -> 18.9 (node visits 14.5 -> 20.1,
+// triangle tests 11.5 -> 19.2), warp instructions -7 %, kernel 1.85 -> 1.78 ms, frame 2.465 -> 2.41 ms; but a 1/8
+// band share of the frame (the 8-GPU case) takes 0.537 ms instead of 0.453 ms, and the 27 KB of shared memory per
+// CTA leave L1 with 50 % hits instead of 76 %.  Lane utilisation is evidently not what bounds this kernel (L1
+// throughput 74 % and the ALU pipe 60 % are), so the register-resident kernel stays the default and this one is
+// selected with RTB_FLAG_POOL (or RTB_WF_POOL=1) for A/B runs; both produce the same bits.
+// ---------------------------------------------------------------------------
+constexpr int POOL = 64;                 // rays per warp
+#ifndef POOL_STACK_N
+#define POOL_STACK_N 6
+#endif
+constexpr int POOL_STACK = POOL_STACK_N;   // traversal stack entries per ray in shared memory; deeper ones in HBM
+enum : uint32_t { PS_DEAD = 0u, PS_NODE = 1u, PS_LEAF = 2u, PS_SHADE = 3u };
+// shared-memory words per warp: field-major [field][POOL]
+enum { PF_OX, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_IX, PF_IY, PF_IZ, PF_TBEST, PF_HT,
+       PF_HSLOT, PF_HORIG, PF_CUR, PF_SP, PF_PIX, PF_LEVEL, PF_RNGLO, PF_RNGHI, PF_ST, PF_STACK0,
+       PF_FIELDS = PF_STACK0 + POOL_STACK };
+constexpr int POOL_WORDS = PF_FIELDS * POOL + 32;     // + the deal list
+
+#ifndef POOL_MIN_BLOCKS
+#define POOL_MIN_BLOCKS 8
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK, POOL_MIN_BLOCKS)
+k_wf_bounce_pool(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const float4* __restrict__ qo,
+                 const float4* __restrict__ qd, const uint32_t* __restrict__ n_ptr, uint32_t smp,
+                 uint32_t* __restrict__ work_counter, uint32_t* __restrict__ ovf_base, uint32_t ovf_depth,
+                 const WfTune tune, TraceCounters* __restrict__ counters) {
+    extern __shared__ uint32_t smem_pool[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t* const W = smem_pool + warp * POOL_WORDS;
+    float* const F = reinterpret_cast<float*>(W);
+    uint32_t* const list = W + PF_FIELDS * POOL;
+    uint32_t* const ovf = ovf_base + (size_t)(blockIdx.x * (WF_BLOCK / 32) + warp) * POOL * ovf_depth;
+    const uint32_t n = *n_ptr;
+    const uint32_t root_code = root_code_of(sc);
+    const unsigned lt = (1u << lane) - 1u;
+    bool exhausted = (n == 0u);
+    unsigned long long n_node = 0, n_tri = 0, n_rays = 0;
+    W[PF_ST * POOL + lane] = PS_DEAD; W[PF_ST * POOL + lane + 32] = PS_DEAD;
+    __syncwarp();
+    const uint32_t node_min = tune.pool_node_min;
+
+    // (re)start the ray of pooled slot `p`
+    auto put_ray = [&](uint32_t p, V3 o, V3 d) {
+        F[PF_OX * POOL + p] = o.x; F[PF_OY * POOL + p] = o.y; F[PF_OZ * POOL + p] = o.z;
+        F[PF_DX * POOL + p] = d.x; F[PF_DY * POOL + p] = d.y; F[PF_DZ * POOL + p] = d.z;
+        F[PF_IX * POOL + p] = fminf(fmaxf(1.0f / d.x, -1e30f), 1e30f);
+        F[PF_IY * POOL + p] = fminf(fmaxf(1.0f / d.y, -1e30f), 1e30f);
+        F[PF_IZ * POOL + p] = fminf(fmaxf(1.0f / d.z, -1e30f), 1e30f);
+        F[PF_TBEST * POOL + p] = FLT_MAX; F[PF_HT * POOL + p] = FLT_MAX;
+        W[PF_HSLOT * POOL + p] = 0xffffffffu; W[PF_HORIG * POOL + p] = 0xffffffffu;
+        W[PF_CUR * POOL + p] = root_code; W[PF_SP * POOL + p] = 0u;
+        W[PF_ST * POOL + p] = PS_NODE;
+    };
+
+    for (;;) {
+        const uint32_t s0 = W[PF_ST * POOL + lane], s1 = W[PF_ST * POOL + lane + 32];
+        const unsigned dead0 = __ballot_sync(FULL, s0 == PS_DEAD), dead1 = __ballot_sync(FULL, s1 == PS_DEAD);
+        const unsigned node0 = __ballot_sync(FULL, s0 == PS_NODE), node1 = __ballot_sync(FULL, s1 == PS_NODE);
+        const unsigned leaf0 = __ballot_sync(FULL, s0 == PS_LEAF), leaf1 = __ballot_sync(FULL, s1 == PS_LEAF);
+        const unsigned shd0 = __ballot_sync(FULL, s0 == PS_SHADE), shd1 = __ballot_sync(FULL, s1 == PS_SHADE);
+        const uint32_t n_dead = __popc(dead0) + __popc(dead1), n_nodew = __popc(node0) + __popc(node1);
+        const uint32_t n_leafw = __popc(leaf0) + __popc(leaf1), n_shade = __popc(shd0) + __popc(shd1);
+        if (n_dead == (uint32_t)POOL && exhausted) break;
+
+        // ---- refill: every dead slot takes the next path of the bounce queue ----
+        if (!exhausted && (n_dead >= tune.refill_min || n_dead == (uint32_t)POOL)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work_counter, n_dead);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n) { exhausted = true; continue; }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool dead = h ? (s1 == PS_DEAD) : (s0 == PS_DEAD);
+                const uint32_t idx = base + (h ? __popc(dead0) + __popc(dead1 & lt) : __popc(dead0 & lt));
+                if (dead && idx < n) {
+                    const uint32_t p = lane + 32u * h;
+                    const float4 ro = __ldcs(qo + idx), rd = __ldcs(qd + idx);
+                    const uint32_t pix = __float_as_uint(ro.w);
+                    const unsigned long long rs = pb.rng_state[pix];
+                    W[PF_PIX * POOL + p] = pix; W[PF_LEVEL * POOL + p] = 1u;
+                    W[PF_RNGLO * POOL + p] = (uint32_t)rs; W[PF_RNGHI * POOL + p] = (uint32_t)(rs >> 32);
+                    put_ray(p, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z));
+                    ++n_rays;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // ---- pick the step kind with the most candidates and deal the candidates out to the lanes ----
+        uint32_t kind = PS_NODE, m0 = node0, m1 = node1, cnt = n_nodew;
+        if (n_leafw > cnt) { kind = PS_LEAF; m0 = leaf0; m1 = leaf1; cnt = n_leafw; }
+        if (n_shade > cnt || (cnt == 0u)) { kind = PS_SHADE; m0 = shd0; m1 = shd1; cnt = n_shade; }
+        if (cnt == 0u) continue;                      // cannot happen: some slot is alive
+        {
+            const uint32_t r0 = __popc(m0 & lt), r1 = __popc(m0) + __popc(m1 & lt);
+            if (((m0 >> lane) & 1u) && r0 < 32u) list[r0] = lane;
+            if (((m1 >> lane) & 1u) && r1 < 32u) list[r1] = lane + 32u;
+        }
+        __syncwarp();
+        const bool have = lane < min(cnt, 32u);
+        const uint32_t p = have ? list[lane] : 0u;
+        __syncwarp();
+
+        if (kind == PS_NODE) {
+            // ---- up to descend_max BVH4 node visits for the dealt rays ----
+            float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, tbest = 0.f;
+            uint32_t cur = 0u, sp = 0u;
+            bool go = have;
+            if (have) {
+                ix = F[PF_IX * POOL + p]; iy = F[PF_IY * POOL + p]; iz = F[PF_IZ * POOL + p];
+                ox = -F[PF_OX * POOL + p] * ix; oy = -F[PF_OY * POOL + p] * iy; oz = -F[PF_OZ * POOL + p] * iz;
+                tbest = F[PF_TBEST * POOL + p];
+                cur = W[PF_CUR * POOL + p]; sp = W[PF_SP * POOL + p];
+            }
+            uint32_t st = PS_NODE;
+#pragma unroll 1
+            for (uint32_t it = 0; it < tune.descend_max; ++it) {
+                // re-deal as soon as too few of the dealt rays still want a node (the others reached a leaf or ended)
+                if ((uint32_t)__popc(__ballot_sync(FULL, go)) < (it == 0u ? 1u : node_min)) break;
+                if (!go) continue;
+                const float4* np = sc.nodes4 + 8u * cur;
+                const float4 lx = __ldg(np + 0), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3);
+                const float4 lz = __ldg(np + 4), hz = __ldg(np + 5);
+                const uint4 cd = __ldg(reinterpret_cast<const uint4*>(np + 6));
+                if (STATS) n_node += 4;
+                const float INF = __int_as_float(0x7f800000);
+                float key[4];
+                uint32_t code[4] = {cd.x, cd.y, cd.z, cd.w};
+#define RTB_SLAB(c, LX, HX, LY, HY, LZ, HZ)                                                             \
+                {                                                                                       \
+                    const float x0 = fmaf(LX, ix, ox), x1 = fmaf(HX, ix, ox);                           \
+                    const float y0 = fmaf(LY, iy, oy), y1 = fmaf(HY, iy, oy);                           \
+                    const float z0 = fmaf(LZ, iz, oz), z1 = fmaf(HZ, iz, oz);                           \
+                    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f)); \
+                    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.0000005f; \
+                    key[c] = ((tn <= tf) && (tn <= tbest)) ? tn : INF;                                  \
+                }
+                RTB_SLAB(0, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x)
+                RTB_SLAB(1, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y)
+                RTB_SLAB(2, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z)
+                RTB_SLAB(3, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w)
+#undef RTB_SLAB
+#define RTB_CE(a, b)                                                                          \
+                {                                                                             \
+                    const bool sw = key[a] > key[b];                                          \
+                    const float ka = sw ? key[b] : key[a], kb = sw ? key[a] : key[b];         \
+                    const uint32_t ca_ = sw ? code[b] : code[a], cb_ = sw ? code[a] : code[b]; \
+                    key[a] = ka; key[b] = kb; code[a] = ca_; code[b] = cb_;                   \
+                }
+                RTB_CE(0, 1) RTB_CE(2, 3) RTB_CE(0, 2) RTB_CE(1, 3) RTB_CE(1, 2)
+#undef RTB_CE
+                auto push = [&](uint32_t c) {
+                    if (sp < (uint32_t)POOL_STACK) W[(PF_STACK0 + sp) * POOL + p] = c;
+                    else ovf[(size_t)p * ovf_depth + (sp - POOL_STACK)] = c;
+                    ++sp;
+                };
+                if (key[0] == INF) {
+                    if (sp == 0u) { st = PS_SHADE; go = false; }       // the ray is finished
+                    else {
+                        --sp;
+                        cur = sp < (uint32_t)POOL_STACK ? W[(PF_STACK0 + sp) * POOL + p] : ovf[(size_t)p * ovf_depth + (sp - POOL_STACK)];
+                    }
+                } else {
+                    cur = code[0];
+                    if (key[3] < INF) push(code[3]);
+                    if (key[2] < INF) push(code[2]);
+                    if (key[1] < INF) push(code[1]);
+                }
+                if (go && (cur & LEAF_FLAG)) { st = PS_LEAF; go = false; }
+            }
+            if (have) { W[PF_CUR * POOL + p] = cur; W[PF_SP * POOL + p] = sp; W[PF_ST * POOL + p] = st; }
+        } else if (kind == PS_LEAF) {
+            // ---- the exact tests of one leaf per dealt ray (get_box_min_time_intersection, raytrace.rs:1013-1050) ----
+            if (have) {
+                const V3 o = mk(F[PF_OX * POOL + p], F[PF_OY * POOL + p], F[PF_OZ * POOL + p]);
+                const V3 d = mk(F[PF_DX * POOL + p], F[PF_DY * POOL + p], F[PF_DZ * POOL + p]);
+                float ht = F[PF_HT * POOL + p], tbest = F[PF_TBEST * POOL + p];
+                int hslot = (int)W[PF_HSLOT * POOL + p];
+                uint32_t horig = W[PF_HORIG * POOL + p];
+                uint32_t cur = W[PF_CUR * POOL + p], sp = W[PF_SP * POOL + p];
+                const uint32_t first = (cur & ~LEAF_FLAG) >> 3, cnt_t = cur & 7u;
+                const float4* q = sc.tri + (size_t)RTB_TRI_F4 * first;
+                float4 a0 = __ldg(q), a1 = __ldg(q + 1);
+                for (uint32_t k = first; k < first + cnt_t; ++k, q += RTB_TRI_F4) {
+                    float t;
+                    if (STATS) ++n_tri;
+                    const float4 c0 = a0, c1 = a1;
+                    if (k + 1u < first + cnt_t) { a0 = __ldg(q + RTB_TRI_F4); a1 = __ldg(q + RTB_TRI_F4 + 1); }
+                    if (tri_test_pre(q, c0, c1, o, d, hslot >= 0, ht, &t)) {
+                        const uint32_t orig = __float_as_uint(c1.w);
+                        if (hslot < 0 || t < ht || (t == ht && orig < horig)) {
+                            ht = t; hslot = (int)k; horig = orig;
+                            if (t < tbest) tbest = t;      // a NaN t never tightens the bound
+                        }
+                    }
+                }
+                uint32_t st = PS_SHADE;
+                if (sp != 0u) {
+                    --sp;
+                    cur = sp < (uint32_t)POOL_STACK ? W[(PF_STACK0 + sp) * POOL + p] : ovf[(size_t)p * ovf_depth + (sp - POOL_STACK)];
+                    st = (cur & LEAF_FLAG) ? PS_LEAF : PS_NODE;
+                }
+                F[PF_HT * POOL + p] = ht; F[PF_TBEST * POOL + p] = tbest;
+                W[PF_HSLOT * POOL + p] = (uint32_t)hslot; W[PF_HORIG * POOL + p] = horig;
+                W[PF_CUR * POOL + p] = cur; W[PF_SP * POOL + p] = sp; W[PF_ST * POOL + p] = st;
+            }
+        } else {
+            // ---- project_ray :1283-1293 for finished rays: bounce again in place or end the path ----
+            if (have) {
+                const V3 o = mk(F[PF_OX * POOL + p], F[PF_OY * POOL + p], F[PF_OZ * POOL + p]);
+                const V3 d = mk(F[PF_DX * POOL + p], F[PF_DY * POOL + p], F[PF_DZ * POOL + p]);
+                const float ht = F[PF_HT * POOL + p];
+                const int hslot = (int)W[PF_HSLOT * POOL + p];
+                const uint32_t pix = W[PF_PIX * POOL + p];
+                uint32_t level = W[PF_LEVEL * POOL + p];
+                Rng g;
+                g.state = (unsigned long long)W[PF_RNGLO * POOL + p] | ((unsigned long long)W[PF_RNGHI * POOL + p] << 32);
+                V3 term = mk(0.f, 0.f, 0.f);
+                bool ended = true;
+                if (hslot < 0) {
+                    term = sky_color();
+                } else {
+                    V3 color, no, nd;
+                    float alpha = 0.f;
+                    if (shade_hit(sc, hslot, ht, o, d, g, &color, &alpha, &no, &nd) == 0) {
+                        term = color;
+                    } else {
+                        pb.stack[(size_t)level * pb.n_slots + pix] = make_float4(color.x, color.y, color.z, alpha);
+                        ++level;
+                        if (level < vw.maxdepth) {          // project_ray(depth-1) with depth-1 > 0
+                            W[PF_LEVEL * POOL + p] = level;
+                            W[PF_RNGLO * POOL + p] = (uint32_t)g.state; W[PF_RNGHI * POOL + p] = (uint32_t)(g.state >> 32);
+                            put_ray(p, no, nd);
+                            ended = false; ++n_rays;
+                        }                                   // else depth 0: black (:1261), not counted
+                    }
+                }
+                if (ended) { finish_path(vw, pb, pix, smp, level, term); W[PF_ST * POOL + p] = PS_DEAD; }
+            }
+        }
+        __syncwarp();
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        n_rays += __shfl_xor_sync(FULL, n_rays, off);
+        if (STATS) {
+            n_node += __shfl_xor_sync(FULL, n_node, off);
+            n_tri += __shfl_xor_sync(FULL, n_tri, off);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&counters->rays, n_rays);
+        if (STATS) {
+            atomicAdd(&counters->node_tests, n_node); atomicAdd(&counters->tri_tests, n_tri);
+            atomicAdd(&counters->node_tests_bounce, n_node); atomicAdd(&counters->tri_tests_bounce, n_tri);
+        }
+    }
+}
+
 // per-sample reset of the queue / work counters
 struct WfCounters {
     uint32_t n_bounce;        // size of the bounce queue
@@ -500,8 +771,12 @@ __global__ void k_wf_tally(WfCounters* c) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample) {
+static uint32_t pool_ovf_depth(uint32_t stack4) { return stack4 > (uint32_t)POOL_STACK ? stack4 - POOL_STACK : 1u; }
+static constexpr size_t POOL_MAX_WARPS = 148 * 8 * (WF_BLOCK / 32) * 2;   // resident warps of a B200, with slack
+
+size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample, uint32_t stack4) {
     size_t b = 0;
+    b += sizeof(uint32_t) * POOL_MAX_WARPS * POOL * pool_ovf_depth(stack4) + 256;   // pool kernel: deep stack entries
     b += 2 * (sizeof(float4) * (size_t)n_slots + 256);          // bounce ray queue (o, d)
     b += sizeof(float2) * (size_t)n_slots + 256;                // hit records of the primary rays
     b += sizeof(float4) * (size_t)n_slots * maxdepth + 256;     // mix stacks
@@ -529,6 +804,7 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     pb.acc = multi ? (float4*)take(sizeof(float4) * n_slots) : nullptr;
     pb.rgba = d_rgba; pb.prim_out = d_prim; pb.t_out = d_t; pb.n_slots = n_slots;
     WfCounters* wc = (WfCounters*)take(sizeof(WfCounters));
+    uint32_t* pool_ovf = (uint32_t*)take(sizeof(uint32_t) * POOL_MAX_WARPS * POOL * pool_ovf_depth(sc.stack4));
 
     // persistent grids: as many CTAs as fit, given the shared-memory traversal stacks (3 entries per BVH4 level, 4 B each, per thread)
     const bool stats = (vw.flags & RTB_FLAG_STATS) != 0;
@@ -565,8 +841,23 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
         refill_min_p = e3 ? (uint32_t)std::min(32, std::max(1, atoi(e3))) : WF_REFILL_MIN_PRIMARY;
     }
 
-    const WfTune tune = {descend_max, refill_min, smem_depth};
-    const WfTune tune_p = {descend_max, refill_min_p, smem_depth};
+    static int use_pool = -1;
+    if (use_pool < 0) { const char* e = getenv("RTB_WF_POOL"); use_pool = e ? atoi(e) : 0; }
+    const bool pool = (use_pool != 0 || (vw.flags & RTB_FLAG_POOL)) && !brute;
+    const size_t smem_pool_bytes = sizeof(uint32_t) * (WF_BLOCK / 32) * POOL_WORDS;
+    int grid_p = 0;
+    if (pool) {
+        int per_sm = 0;
+        if (stats) RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_bounce_pool<true>, WF_BLOCK, smem_pool_bytes));
+        else RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_bounce_pool<false>, WF_BLOCK, smem_pool_bytes));
+        { const char* e = getenv("RTB_POOL_CTAS"); if (e) per_sm = std::min(per_sm, std::max(1, atoi(e))); }
+        grid_p = sms * std::max(per_sm, 1);
+        if ((size_t)grid_p * (WF_BLOCK / 32) > POOL_MAX_WARPS) grid_p = (int)(POOL_MAX_WARPS / (WF_BLOCK / 32));
+    }
+    static int pool_node_min = -1;
+    if (pool_node_min < 0) { const char* e = getenv("RTB_POOL_NODE_MIN"); pool_node_min = e ? atoi(e) : 1; }
+    const WfTune tune = {descend_max, refill_min, smem_depth, (uint32_t)pool_node_min};
+    const WfTune tune_p = {descend_max, refill_min_p, smem_depth, 1u};
     RTB_CUDA(cudaMemsetAsync(wc, 0, sizeof(WfCounters), stream));
     auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], stream); };
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
@@ -580,7 +871,13 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
         k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
         mark(3);
         if (launches) *launches += 2;
-        if (vw.maxdepth > 1) {
+        if (vw.maxdepth > 1 && pool) {
+            if (stats)
+                k_wf_bounce_pool<true><<<grid_p, WF_BLOCK, smem_pool_bytes, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, pool_ovf, pool_ovf_depth(sc.stack4), tune, d_counters);
+            else
+                k_wf_bounce_pool<false><<<grid_p, WF_BLOCK, smem_pool_bytes, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, pool_ovf, pool_ovf_depth(sc.stack4), tune, d_counters);
+            if (launches) ++*launches;
+        } else if (vw.maxdepth > 1) {
             if (stats)
                 k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
             else

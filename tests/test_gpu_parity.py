@@ -154,6 +154,23 @@ def test_megakernel_equals_wavefront(R, O, scenes, spp):
     assert_bit_exact(b, bvh.render(O.main_viewport(801, 453, 5, spp), seed=13), f"megakernel spp={spp}")
 
 
+@pytest.mark.parametrize("spp,maxdepth", [(1, 5), (2, 16)])
+def test_pool_bounce_kernel_equals_default(R, O, scenes, spp, maxdepth):
+    """The shared-memory ray-pool variant of the bounce kernel (RTB_FLAG_POOL) is the same function as the default
+    register-resident one: ids, t, colour, ray and test counts; and it matches the oracle."""
+    from rust_raytrace_b200 import _lib
+    s, _, bvh = scenes[False]
+    v = R.main_viewport(1283, 721, maxdepth, spp)
+    a = gpu_render(R, s, v, seed=17, stats=True)
+    vp = _lib.RtbView.from_buffer_copy(v)
+    vp.flags |= _lib.RTB_FLAG_POOL
+    b = gpu_render(R, s, vp, seed=17, stats=True)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+    assert a[3].total_rays == b[3].total_rays
+    assert a[4].stats.node_tests == b[4].stats.node_tests and a[4].stats.tri_tests == b[4].stats.tri_tests
+    assert_bit_exact(b, bvh.render(O.main_viewport(1283, 721, maxdepth, spp), seed=17), f"pool spp={spp}")
+
+
 def test_rotated_camera(R, O, scenes):
     s, _, bvh = scenes[True]
     args = ((400, 300), (1.0, 0.75), [1.0, -1.0, 0.5], None, 60.0, 0.4, 5, 1)
