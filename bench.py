@@ -52,7 +52,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_wf_bounce launch of the teapot4k frame at N=1, from the
 # `ncu --set full` capture summarised in profiles/ (see DESIGN.md "Roofline"); null for every other configuration.
-NCU_TRAFFIC_BOUNCE_TEAPOT4K = 390.3e6
+NCU_TRAFFIC_BOUNCE_TEAPOT4K = 370.4e6   # profiles/r1_v6_k_wf_bounce_raw.csv: 257.6 MB read + 112.8 MB written
 
 
 def measured_peaks():
@@ -167,13 +167,13 @@ def run_reference(args):
     ov = O.main_viewport(W, H, maxdepth, spp)
     # bounded sample per step, sized so that warmup+steps stay within a few minutes whatever the host:
     # ~2 s of work at the rate of a small probe band through the middle of the frame
-    mid = cpu_sample_rows(name)[0]
+    mid = H // 2 + (100 if name == "field1m" else 0)      # the field's teapots fill the lower half of the frame
     probe_rows = 16 if spp == 1 else 1
     _, _, _, probe = osc.render(ov, seed=SEED, threads=cores, rows=(mid, mid + probe_rows), want_ids=False)
     n_rows = int(min(H - mid, max(probe_rows, probe_rows * 2.0 / max(probe.seconds, 1e-3))))
     if spp == 1:
         n_rows = max(8, n_rows // 8 * 8)
-    rows = (mid - n_rows // 2, mid - n_rows // 2 + n_rows) if spp == 1 else (mid, mid + n_rows)
+    rows = (max(0, mid - n_rows // 2), min(H, max(0, mid - n_rows // 2) + n_rows)) if spp == 1 else (mid, min(H, mid + n_rows))
     rates, secs, rays = [], [], 0
     for i in range(args.warmup + args.steps):
         _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
