@@ -828,6 +828,7 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
         RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_wf_trace<false>, WF_BLOCK, smem));
         RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_wf_bounce<false>, WF_BLOCK, smem));
     }
+    { const char* e = getenv("RTB_WF_CTAS"); if (e) { per_sm_t = std::min(per_sm_t, std::max(1, atoi(e))); per_sm_b = std::min(per_sm_b, std::max(1, atoi(e))); } }
     const int grid_t = sms * std::max(per_sm_t, 1), grid_b = sms * std::max(per_sm_b, 1);
     const uint32_t shade_blocks = std::min<uint32_t>((n_slots + 255u) / 256u, 148u * 16u);
     const uint32_t brute = (vw.flags & RTB_FLAG_BRUTE) ? 1u : 0u;
