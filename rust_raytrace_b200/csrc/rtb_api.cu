@@ -215,7 +215,8 @@ int env_int(const char* name, int dflt) {
 // piece's blocks.  after_piece(c, piece_view, lane_stream) runs after a piece's kernels are queued.
 template <class F>
 int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d_rgba, uint32_t* d_prim, float* d_t,
-                  cudaStream_t st, uint32_t pieces, uint32_t n_lanes, uint32_t* launches, uint64_t* primary, F after_piece) {
+                  cudaStream_t st, uint32_t pieces, uint32_t n_lanes, uint32_t* launches, uint64_t* primary, F after_piece,
+                  bool taper = false) {
     pieces = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(pieces, RTB_MAX_CHUNKS), whole.my_tile_rows));
     n_lanes = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(n_lanes, RTB_MAX_LANES), pieces));
     if (whole.flags & RTB_FLAG_MEGAKERNEL) n_lanes = 1;
@@ -235,10 +236,19 @@ int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d
         RTB_CUDA(cudaEventRecord(g.fork_ev, st));
         for (uint32_t l = 1; l < n_lanes; ++l) RTB_CUDA(cudaStreamWaitEvent(g.lanes[l].st, g.fork_ev, 0));
     }
+    // Piece boundaries.  With copies to overlap (taper) the pieces shrink linearly, first : last = (pieces+1) : 2, so the
+    // copy of the last piece — the one nothing can hide — is short.
+    static const bool taper_on = getenv("RTB_PIECE_TAPER") ? atoi(getenv("RTB_PIECE_TAPER")) != 0 : true;
+    auto bound = [&](uint32_t c) -> uint32_t {        // first band of piece c (relative), bound(pieces) = all bands
+        if (!taper || !taper_on || pieces < 3) return (uint32_t)((uint64_t)whole.my_tile_rows * c / pieces);
+        const uint64_t total_w = (uint64_t)pieces * (pieces + 3) / 2;                 // sum of (pieces + 1 - i), i < pieces
+        const uint64_t w = (uint64_t)c * (2 * pieces + 3 - c) / 2;                    // sum over i < c
+        return (uint32_t)((uint64_t)whole.my_tile_rows * w / total_w);
+    };
     for (uint32_t c = 0; c < pieces; ++c) {
         ViewDev vd = whole;
-        vd.band_begin = whole.band_begin + (uint32_t)((uint64_t)whole.my_tile_rows * c / pieces);
-        vd.my_tile_rows = whole.band_begin + (uint32_t)((uint64_t)whole.my_tile_rows * (c + 1) / pieces) - vd.band_begin;
+        vd.band_begin = whole.band_begin + bound(c);
+        vd.my_tile_rows = whole.band_begin + bound(c + 1) - vd.band_begin;
         if (vd.my_tile_rows == 0) continue;
         const uint32_t l = c % n_lanes;
         cudaStream_t ls = l == 0 ? st : g.lanes[l].st;     // lane 0 is the caller's stream itself
@@ -527,7 +537,7 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
             if (prim_out && (rc2 = copy_plane(prim_out, g.d_prim, sizeof(uint32_t))) != RTB_OK) return rc2;
             if (t_out && (rc2 = copy_plane(t_out, g.d_t, sizeof(float))) != RTB_OK) return rc2;
             return RTB_OK;
-        });
+        }, true);
         if (rc != RTB_OK) return rc;
         RTB_CUDA(cudaEventRecord(g.ev1, g.stream));
         return RTB_OK;
