@@ -123,21 +123,22 @@ __device__ __forceinline__ void start_ray(TravState& s, V3 o, V3 d, uint32_t roo
 // Tried and dropped (B200, 4K teapot frame, bounce kernel 2.3 ms): postponing leaves into a per-lane queue so
 // that node visits and triangle tests run in separate, fuller phases — 15-25% slower (more box and triangle
 // tests because t_best tightens later, plus the queue bookkeeping), see DESIGN.md "What did not work".
-template <bool STATS>
+template <bool STATS, bool OVF>
 __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, bool& trav, uint32_t* stack,
                                            uint32_t* ovf, int smem_depth, uint32_t k_nodes, unsigned long long& n_node,
                                            unsigned long long& n_tri) {
-    // The first `smem_depth` stack entries live in shared memory, deeper ones (rare) in thread-local memory:
+    // OVF: the first `smem_depth` stack entries live in shared memory, deeper ones (rare) in thread-local memory
+    // (!OVF: the whole worst-case stack fits in shared memory and the depth tests compile away, ~2 % faster):
     // sizing the shared stack for the worst case (3 entries per BVH4 level, 37 for the teapot scene) took 143 KB
     // of each SM's 256 KB and grows with the tree height (a 1 M-triangle scene would drop to 4 CTAs/SM).  Measured on
     // B200, 4K teapot frame: 40 entries 3.22 ms, 16: 3.21, 12: 3.20, 8: 3.18, 6: 3.15, 4: 3.16 — L1 capacity is not the limiter.
     auto pop = [&]() {
         if (s.sp == 0) { trav = false; return; }
         --s.sp;
-        s.cur = s.sp < smem_depth ? stack[s.sp * WF_BLOCK] : ovf[s.sp - smem_depth];
+        s.cur = (!OVF || s.sp < smem_depth) ? stack[s.sp * WF_BLOCK] : ovf[s.sp - smem_depth];
     };
     auto push = [&](uint32_t code) {
-        if (s.sp < smem_depth) stack[s.sp * WF_BLOCK] = code; else ovf[s.sp - smem_depth] = code;
+        if (!OVF || s.sp < smem_depth) stack[s.sp * WF_BLOCK] = code; else ovf[s.sp - smem_depth] = code;
         ++s.sp;
     };
 #pragma unroll 1
@@ -244,7 +245,7 @@ struct WorkFetch {
 // ---------------------------------------------------------------------------
 // stage 1: closest hit of the primary rays, persistent threads with per-lane refill
 // ---------------------------------------------------------------------------
-template <bool STATS>
+template <bool STATS, bool OVF>
 __global__ void __launch_bounds__(WF_BLOCK, WF_TRACE_MIN_BLOCKS)
 k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
            float2* __restrict__ hit_out, uint32_t* __restrict__ work_counter, uint32_t brute, const WfTune tune,
@@ -253,7 +254,7 @@ k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
     const int smem_depth = tune.smem_depth;
     extern __shared__ uint32_t smem_stack[];
     uint32_t* const stack = smem_stack + threadIdx.x;     // entry k lives at stack[k * WF_BLOCK]
-    uint32_t ovf[WF_OVF];
+    uint32_t ovf[OVF ? WF_OVF : 1];
     const unsigned lane = threadIdx.x & 31u;
     WorkFetch wf;
     wf.exhausted = (n == 0u);
@@ -284,7 +285,7 @@ k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
         for (;;) {
             const bool was = trav;
             if (brute) { if (trav) { brute_scan<STATS>(sc, s, n_tri); trav = false; } }
-            else trav_round<STATS>(sc, s, trav, stack, ovf, smem_depth, descend_max, n_node, n_tri);
+            else trav_round<STATS, OVF>(sc, s, trav, stack, ovf, smem_depth, descend_max, n_node, n_tri);
             if (was && !trav) __stcs(hit_out + ray_id, make_float2(s.h.t, __int_as_float(s.h.slot)));
             const unsigned act = __ballot_sync(FULL, trav);
             if (act == 0u) break;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const SceneDev sc, const ViewD
 // ---------------------------------------------------------------------------
 // stage 3: every bounce path to its end, persistent
 // ---------------------------------------------------------------------------
-template <bool STATS>
+template <bool STATS, bool OVF>
 __global__ void __launch_bounds__(WF_BLOCK, WF_BOUNCE_MIN_BLOCKS)
 k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const float4* __restrict__ qo,
             const float4* __restrict__ qd, const uint32_t* __restrict__ n_ptr, uint32_t smp,
@@ -413,7 +414,7 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
     const int smem_depth = tune.smem_depth;
     extern __shared__ uint32_t smem_stack[];
     uint32_t* const stack = smem_stack + threadIdx.x;
-    uint32_t ovf[WF_OVF];
+    uint32_t ovf[OVF ? WF_OVF : 1];
     const uint32_t n = *n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     WorkFetch wf;
@@ -472,7 +473,7 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
         // ---- traversal rounds until enough lanes wait for service ----
         for (;;) {
             if (brute) { if (trav) { brute_scan<STATS>(sc, s, n_tri); trav = false; } }
-            else trav_round<STATS>(sc, s, trav, stack, ovf, smem_depth, descend_max, n_node, n_tri);
+            else trav_round<STATS, OVF>(sc, s, trav, stack, ovf, smem_depth, descend_max, n_node, n_tri);
             const unsigned act = __ballot_sync(FULL, trav);
             if (act == 0u || (32u - __popc(act)) >= refill_min) break;
         }
@@ -819,24 +820,27 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     const bool stats = (vw.flags & RTB_FLAG_STATS) != 0;
     static int smem_stack_cfg = -1;
     if (smem_stack_cfg < 0) { const char* e = getenv("RTB_WF_STACK"); smem_stack_cfg = e ? std::max(1, atoi(e)) : WF_SMEM_STACK; }
-    const int smem_depth = std::min<int>((int)sc.stack4, smem_stack_cfg);
+    // the whole worst-case stack in shared memory when 8 CTAs of it fit an SM (<= 24 KB per CTA), else 8 entries + overflow
+    const bool ovf = getenv("RTB_WF_STACK") != nullptr || (size_t)sc.stack4 * WF_BLOCK * sizeof(uint32_t) > 24u * 1024u;
+    const int smem_depth = ovf ? std::min<int>((int)sc.stack4, smem_stack_cfg) : (int)sc.stack4;
     const size_t smem = (size_t)smem_depth * WF_BLOCK * sizeof(uint32_t);
     int dev = 0, sms = 0, per_sm_t = 0, per_sm_b = 0;
     RTB_CUDA(cudaGetDevice(&dev));
     RTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // kernel variants: <STATS, OVF>
+    typedef void (*TraceFn)(const SceneDev, const ViewDev, uint32_t, uint32_t, float2*, uint32_t*, uint32_t, const WfTune, TraceCounters*);
+    typedef void (*BounceFn)(const SceneDev, const ViewDev, const PathBuffers, const float4*, const float4*, const uint32_t*, uint32_t,
+                             uint32_t*, uint32_t, const WfTune, TraceCounters*);
+    const TraceFn trace_fn = stats ? (ovf ? k_wf_trace<true, true> : k_wf_trace<true, false>)
+                                   : (ovf ? k_wf_trace<false, true> : k_wf_trace<false, false>);
+    const BounceFn bounce_fn = stats ? (ovf ? k_wf_bounce<true, true> : k_wf_bounce<true, false>)
+                                     : (ovf ? k_wf_bounce<false, true> : k_wf_bounce<false, false>);
     if (smem > 48 * 1024) {
-        RTB_CUDA(cudaFuncSetAttribute(k_wf_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RTB_CUDA(cudaFuncSetAttribute(k_wf_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RTB_CUDA(cudaFuncSetAttribute(k_wf_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RTB_CUDA(cudaFuncSetAttribute(k_wf_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTB_CUDA(cudaFuncSetAttribute(trace_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTB_CUDA(cudaFuncSetAttribute(bounce_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (stats) {
-        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_wf_trace<true>, WF_BLOCK, smem));
-        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_wf_bounce<true>, WF_BLOCK, smem));
-    } else {
-        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_wf_trace<false>, WF_BLOCK, smem));
-        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_wf_bounce<false>, WF_BLOCK, smem));
-    }
+    RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, trace_fn, WF_BLOCK, smem));
+    RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bounce_fn, WF_BLOCK, smem));
     { const char* e = getenv("RTB_WF_CTAS"); if (e) { per_sm_t = std::min(per_sm_t, std::max(1, atoi(e))); per_sm_b = std::min(per_sm_b, std::max(1, atoi(e))); } }
     const int grid_t = sms * std::max(per_sm_t, 1), grid_b = sms * std::max(per_sm_b, 1);
     const uint32_t shade_blocks = std::min<uint32_t>((n_slots + 255u) / 256u, 148u * 16u);
@@ -873,10 +877,7 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
         mark(0);
         mark(1);
-        if (stats)
-            k_wf_trace<true><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune_p, d_counters);
-        else
-            k_wf_trace<false><<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune_p, d_counters);
+        trace_fn<<<grid_t, WF_BLOCK, smem, stream>>>(sc, vw, smp, n_slots, hit, &wc->work_primary, brute, tune_p, d_counters);
         mark(2);
         k_wf_shade<<<shade_blocks, 256, 0, stream>>>(sc, vw, pb, hit, n_slots, smp, qo1, qd1, &wc->n_bounce);
         mark(3);
@@ -888,10 +889,7 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
                 k_wf_bounce_pool<false><<<grid_p, WF_BLOCK, smem_pool_bytes, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, pool_ovf, pool_ovf_depth(sc.stack4), tune, d_counters);
             if (launches) ++*launches;
         } else if (vw.maxdepth > 1) {
-            if (stats)
-                k_wf_bounce<true><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
-            else
-                k_wf_bounce<false><<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
+            bounce_fn<<<grid_b, WF_BLOCK, smem, stream>>>(sc, vw, pb, qo1, qd1, &wc->n_bounce, smp, &wc->work_bounce, brute, tune, d_counters);
             if (launches) ++*launches;
         }
         mark(4);
