@@ -185,7 +185,7 @@ int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd
         return rtb_launch_trace(scene_dev(g, n_prims), vd, d_rgba, d_prim, d_t, g.d_counters, st, launches);
     const uint32_t n_slots = vd.my_tile_rows * 2u * ((vd.width + 7u) / 8u) * 32u;
     const size_t need = rtb_wf_workspace_bytes(n_slots, vd.maxdepth ? vd.maxdepth : 1, (vd.s_end - vd.s_begin) > 1,
-                                               scene_dev(g, n_prims).stack4);
+                                               scene_dev(g, n_prims).stack4, vd.flags);
     if (lane.ws_bytes < need) {
         RTB_CUDA(cudaDeviceSynchronize());
         if (lane.d_ws) RTB_CUDA(cudaFree(lane.d_ws));

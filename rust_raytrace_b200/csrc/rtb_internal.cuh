@@ -159,7 +159,7 @@ int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint
 // ---- implemented in rtb_wavefront.cu -------------------------------------------
 // The default renderer: raygen / persistent trace / shade+compact stages per bounce level.
 // counters->rays receives the BOUNCE rays only; the caller adds the primary rays (valid pixels x samples).
-size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample, uint32_t stack4);
+size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample, uint32_t stack4, uint32_t flags);
 // stage_ev (nullable): 5 events recorded at the stage boundaries of every sample; stage_ms accumulates their gaps
 // (this synchronises the stream once per sample: timing mode only).
 int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace, float4* d_rgba, uint32_t* d_prim,

@@ -669,15 +669,19 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     RTB_CUDA(children.alloc(n_int)); RTB_CUDA(range.alloc(n_int)); RTB_CUDA(parent.alloc(n_all));
     RTB_CUDA(flags4.alloc(n_int + 1)); RTB_CUDA(idx4.alloc(n_int + 1));
     RTB_CUDA(kind.alloc(n_all));
-    static int builder = -1, ploc_r = 0, sah_leaves = 0;
-    if (builder < 0) {
-        const char* e = getenv("RTB_BUILDER");       // "karras" = plain radix tree, default PLOC
-        builder = (e && e[0] == 'k') ? 0 : 1;
+    // experiment knobs, read once (thread-safe function-local static)
+    struct BuildEnv { int builder, ploc_r, sah_leaves; };
+    static const BuildEnv benv = [] {
+        BuildEnv e;
+        const char* b = getenv("RTB_BUILDER");        // "karras" = plain radix tree, default PLOC
+        e.builder = (b && b[0] == 'k') ? 0 : 1;
         const char* r = getenv("RTB_PLOC_R");
-        ploc_r = r ? std::min(PLOC_R_MAX, std::max(1, atoi(r))) : 16;
+        e.ploc_r = r ? std::min(PLOC_R_MAX, std::max(1, atoi(r))) : 16;
         const char* l = getenv("RTB_SAH_LEAVES");
-        sah_leaves = l ? atoi(l) : 1;
-    }
+        e.sah_leaves = l ? atoi(l) : 1;
+        return e;
+    }();
+    const int builder = benv.builder, ploc_r = benv.ploc_r, sah_leaves = benv.sah_leaves;
     const bool use_ploc = builder == 1 && n_int > 0 && !force_karras;
     if (use_ploc) {
         RTB_CUDA(pstate.alloc(2)); RTB_CUDA(qlo.alloc(n_all)); RTB_CUDA(qhi.alloc(n_all));

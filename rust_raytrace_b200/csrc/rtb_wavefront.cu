@@ -781,12 +781,41 @@ __global__ void k_wf_tally(WfCounters* c) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// Experiment knobs, read from the environment once (function-local static: thread-safe, the multi-GPU entry points call
+// the launcher from one host thread per GPU).  Defaults are the measured optima quoted next to the constants above.
+struct WfEnv {
+    uint32_t descend_max, refill_min, refill_min_primary, pool_node_min;
+    int smem_stack;          // > 0: force the bounded shared-memory stack with this many entries (+ overflow)
+    int ctas, pool_ctas;     // > 0: cap on resident CTAs per SM (persistent grids)
+    bool pool;               // RTB_WF_POOL=1: ray-pool bounce kernel for every frame
+    static int geti(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+    static const WfEnv& get() {
+        static const WfEnv env = [] {
+            WfEnv e;
+            e.descend_max = (uint32_t)std::max(1, geti("RTB_WF_DESCEND", (int)WF_DESCEND_MAX));
+            e.refill_min = (uint32_t)std::min(32, std::max(1, geti("RTB_WF_REFILL", (int)WF_REFILL_MIN)));
+            e.refill_min_primary = (uint32_t)std::min(32, std::max(1, geti("RTB_WF_REFILL_P", (int)WF_REFILL_MIN_PRIMARY)));
+            e.pool_node_min = (uint32_t)std::max(1, geti("RTB_POOL_NODE_MIN", 1));
+            e.smem_stack = geti("RTB_WF_STACK", 0);
+            e.ctas = geti("RTB_WF_CTAS", 0);
+            e.pool_ctas = geti("RTB_POOL_CTAS", 0);
+            e.pool = geti("RTB_WF_POOL", 0) != 0;
+            return e;
+        }();
+        return env;
+    }
+};
+
 static uint32_t pool_ovf_depth(uint32_t stack4) { return stack4 > (uint32_t)POOL_STACK ? stack4 - POOL_STACK : 1u; }
 static constexpr size_t POOL_MAX_WARPS = 148 * 8 * (WF_BLOCK / 32) * 2;   // resident warps of a B200, with slack
 
-size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample, uint32_t stack4) {
+static bool pool_selected(uint32_t flags) {
+    return (WfEnv::get().pool || (flags & RTB_FLAG_POOL)) && !(flags & RTB_FLAG_BRUTE);
+}
+
+size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample, uint32_t stack4, uint32_t flags) {
     size_t b = 0;
-    b += sizeof(uint32_t) * POOL_MAX_WARPS * POOL * pool_ovf_depth(stack4) + 256;   // pool kernel: deep stack entries
+    if (pool_selected(flags)) b += sizeof(uint32_t) * POOL_MAX_WARPS * POOL * pool_ovf_depth(stack4) + 256;   // deep stack entries
     b += 2 * (sizeof(float4) * (size_t)n_slots + 256);          // bounce ray queue (o, d)
     b += sizeof(float2) * (size_t)n_slots + 256;                // hit records of the primary rays
     b += sizeof(float4) * (size_t)n_slots * maxdepth + 256;     // mix stacks
@@ -814,15 +843,15 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     pb.acc = multi ? (float4*)take(sizeof(float4) * n_slots) : nullptr;
     pb.rgba = d_rgba; pb.prim_out = d_prim; pb.t_out = d_t; pb.n_slots = n_slots;
     WfCounters* wc = (WfCounters*)take(sizeof(WfCounters));
-    uint32_t* pool_ovf = (uint32_t*)take(sizeof(uint32_t) * POOL_MAX_WARPS * POOL * pool_ovf_depth(sc.stack4));
+    const bool pool = pool_selected(vw.flags);
+    uint32_t* pool_ovf = pool ? (uint32_t*)take(sizeof(uint32_t) * POOL_MAX_WARPS * POOL * pool_ovf_depth(sc.stack4)) : nullptr;
+    const WfEnv& env = WfEnv::get();
 
     // persistent grids: as many CTAs as fit, given the shared-memory traversal stacks (3 entries per BVH4 level, 4 B each, per thread)
     const bool stats = (vw.flags & RTB_FLAG_STATS) != 0;
-    static int smem_stack_cfg = -1;
-    if (smem_stack_cfg < 0) { const char* e = getenv("RTB_WF_STACK"); smem_stack_cfg = e ? std::max(1, atoi(e)) : WF_SMEM_STACK; }
     // the whole worst-case stack in shared memory when 8 CTAs of it fit an SM (<= 24 KB per CTA), else 8 entries + overflow
-    const bool ovf = getenv("RTB_WF_STACK") != nullptr || (size_t)sc.stack4 * WF_BLOCK * sizeof(uint32_t) > 24u * 1024u;
-    const int smem_depth = ovf ? std::min<int>((int)sc.stack4, smem_stack_cfg) : (int)sc.stack4;
+    const bool ovf = env.smem_stack > 0 || (size_t)sc.stack4 * WF_BLOCK * sizeof(uint32_t) > 24u * 1024u;
+    const int smem_depth = ovf ? std::min<int>((int)sc.stack4, env.smem_stack > 0 ? env.smem_stack : WF_SMEM_STACK) : (int)sc.stack4;
     const size_t smem = (size_t)smem_depth * WF_BLOCK * sizeof(uint32_t);
     int dev = 0, sms = 0, per_sm_t = 0, per_sm_b = 0;
     RTB_CUDA(cudaGetDevice(&dev));
@@ -841,37 +870,22 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     }
     RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, trace_fn, WF_BLOCK, smem));
     RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, bounce_fn, WF_BLOCK, smem));
-    { const char* e = getenv("RTB_WF_CTAS"); if (e) { per_sm_t = std::min(per_sm_t, std::max(1, atoi(e))); per_sm_b = std::min(per_sm_b, std::max(1, atoi(e))); } }
+    if (env.ctas > 0) { per_sm_t = std::min(per_sm_t, env.ctas); per_sm_b = std::min(per_sm_b, env.ctas); }
     const int grid_t = sms * std::max(per_sm_t, 1), grid_b = sms * std::max(per_sm_b, 1);
     const uint32_t shade_blocks = std::min<uint32_t>((n_slots + 255u) / 256u, 148u * 16u);
     const uint32_t brute = (vw.flags & RTB_FLAG_BRUTE) ? 1u : 0u;
-    static uint32_t descend_max = 0, refill_min = 0, refill_min_p = 0;
-    if (descend_max == 0) {
-        const char* e1 = getenv("RTB_WF_DESCEND");
-        const char* e2 = getenv("RTB_WF_REFILL");
-        descend_max = e1 ? (uint32_t)std::max(1, atoi(e1)) : WF_DESCEND_MAX;
-        refill_min = e2 ? (uint32_t)std::min(32, std::max(1, atoi(e2))) : WF_REFILL_MIN;
-        const char* e3 = getenv("RTB_WF_REFILL_P");
-        refill_min_p = e3 ? (uint32_t)std::min(32, std::max(1, atoi(e3))) : WF_REFILL_MIN_PRIMARY;
-    }
-
-    static int use_pool = -1;
-    if (use_pool < 0) { const char* e = getenv("RTB_WF_POOL"); use_pool = e ? atoi(e) : 0; }
-    const bool pool = (use_pool != 0 || (vw.flags & RTB_FLAG_POOL)) && !brute;
     const size_t smem_pool_bytes = sizeof(uint32_t) * (WF_BLOCK / 32) * POOL_WORDS;
     int grid_p = 0;
     if (pool) {
         int per_sm = 0;
         if (stats) RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_bounce_pool<true>, WF_BLOCK, smem_pool_bytes));
         else RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_bounce_pool<false>, WF_BLOCK, smem_pool_bytes));
-        { const char* e = getenv("RTB_POOL_CTAS"); if (e) per_sm = std::min(per_sm, std::max(1, atoi(e))); }
+        if (env.pool_ctas > 0) per_sm = std::min(per_sm, env.pool_ctas);
         grid_p = sms * std::max(per_sm, 1);
         if ((size_t)grid_p * (WF_BLOCK / 32) > POOL_MAX_WARPS) grid_p = (int)(POOL_MAX_WARPS / (WF_BLOCK / 32));
     }
-    static int pool_node_min = -1;
-    if (pool_node_min < 0) { const char* e = getenv("RTB_POOL_NODE_MIN"); pool_node_min = e ? atoi(e) : 1; }
-    const WfTune tune = {descend_max, refill_min, smem_depth, (uint32_t)pool_node_min};
-    const WfTune tune_p = {descend_max, refill_min_p, smem_depth, 1u};
+    const WfTune tune = {env.descend_max, env.refill_min, smem_depth, env.pool_node_min};
+    const WfTune tune_p = {env.descend_max, env.refill_min_primary, smem_depth, 1u};
     RTB_CUDA(cudaMemsetAsync(wc, 0, sizeof(WfCounters), stream));
     auto mark = [&](int k) { if (stage_ev) cudaEventRecord(stage_ev[k], stream); };
     for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
