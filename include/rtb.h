@@ -126,6 +126,9 @@ typedef struct RtbSceneInfo {
     double   ms_build;        /* LBVH build (morton, sort, hierarchy, refit, emit), device time */
     uint32_t build_launches;
     uint32_t n_gpus;
+    uint32_t n_refs;          /* primitive references in the BVH (>= n_prims: a primitive whose box is long compared
+                                 to the scene is entered as several references with clipped boxes) */
+    uint32_t reserved;
 } RtbSceneInfo;
 
 typedef struct rtb_scene rtb_scene;
@@ -147,7 +150,7 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
                      rtb_scene** out);
 int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* out);
 void rtb_scene_destroy(rtb_scene* s);
-/* Debug/inspection: copy the BVH of GPU 0 back (nodes: n_nodes*8 floats; prim_order: n_prims u32
+/* Debug/inspection: copy the BVH of GPU 0 back (nodes: n_nodes*8 floats; prim_order: n_refs u32
  * = original triangle index of each leaf-order slot).  Either pointer may be NULL. */
 int rtb_scene_download_bvh(const rtb_scene* s, float* nodes, uint32_t* prim_order);
 

@@ -87,6 +87,8 @@ class RtbSceneInfo(C.Structure):
         ("ms_build", C.c_double),
         ("build_launches", C.c_uint32),
         ("n_gpus", C.c_uint32),
+        ("n_refs", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

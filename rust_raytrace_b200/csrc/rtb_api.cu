@@ -386,6 +386,7 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
             s->info.tree_height = br.tree_height;
             for (int k = 0; k < 3; ++k) { s->info.scene_lo[k] = br.lo[k]; s->info.scene_hi[k] = br.hi[k]; }
             s->info.build_launches = br.launches;
+            s->info.n_refs = br.n_refs;
         }
         s->info.ms_upload = std::max(s->info.ms_upload, t1 - t0);
         s->info.ms_build = std::max(s->info.ms_build, (double)br.ms_build);
@@ -411,8 +412,8 @@ int rtb_scene_download_bvh(const rtb_scene* s, float* nodes, uint32_t* prim_orde
     const GpuScene& g = s->gpu[0];
     RTB_CUDA(cudaSetDevice(g.device));
     if (nodes) RTB_CUDA(cudaMemcpy(nodes, g.d_nodes, sizeof(float4) * 2 * g.n_nodes, cudaMemcpyDeviceToHost));
-    if (prim_order && s->info.n_prims)
-        RTB_CUDA(cudaMemcpy(prim_order, g.d_prim_order, sizeof(uint32_t) * s->info.n_prims, cudaMemcpyDeviceToHost));
+    if (prim_order && s->info.n_refs)
+        RTB_CUDA(cudaMemcpy(prim_order, g.d_prim_order, sizeof(uint32_t) * s->info.n_refs, cudaMemcpyDeviceToHost));
     return RTB_OK;
 }
 
@@ -444,7 +445,7 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
         pieces = 1; n_lanes = 1;
         for (float& m : g.lanes[0].stage_ms) m = 0.f;
     }
-    rc = render_pieces(g, s->info.n_prims, vd, (float4*)d_rgba, d_prim, d_t, st, pieces, n_lanes, &launches, &primary,
+    rc = render_pieces(g, s->info.n_refs, vd, (float4*)d_rgba, d_prim, d_t, st, pieces, n_lanes, &launches, &primary,
                        [](uint32_t, const ViewDev&, cudaStream_t) { return (int)RTB_OK; });
     if (rc != RTB_OK) return rc;
     if (stats) {
@@ -506,7 +507,7 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
         const uint32_t n_lanes = (uint32_t)env_int("RTB_LANES", RTB_DEFAULT_LANES);
         RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), g.stream));
         RTB_CUDA(cudaEventRecord(g.ev0, g.stream));
-        rc = render_pieces(g, s->info.n_prims, whole, g.d_rgba, prim_out ? g.d_prim : nullptr, t_out ? g.d_t : nullptr,
+        rc = render_pieces(g, s->info.n_refs, whole, g.d_rgba, prim_out ? g.d_prim : nullptr, t_out ? g.d_t : nullptr,
                            g.stream, pieces, n_lanes, &launches, &primary_total,
                            [&](uint32_t c, const ViewDev& vd, cudaStream_t ls) -> int {
             // the piece's bands go home on the copy stream as soon as its kernels are done
@@ -620,7 +621,7 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
         } else {
             ViewDev vd = make_view(v, 0, 1, false);
             uint64_t primary = 0;
-            rc = launch_frame(g, g.lanes[0], s->info.n_prims, vd, g.d_rgba, nullptr, nullptr, g.stream, &launches, &primary);
+            rc = launch_frame(g, g.lanes[0], s->info.n_refs, vd, g.d_rgba, nullptr, nullptr, g.stream, &launches, &primary);
             if (rc != RTB_OK) return rc;
             primary_total += primary;
         }

@@ -139,6 +139,7 @@ struct BuildResult {
     float4* d_shade = nullptr;
     uint32_t* d_prim_order = nullptr;
     uint32_t n_nodes = 0, n_leaves = 0, max_leaf = 0, tree_height = 0;
+    uint32_t n_refs = 0;             // primitive references in the tree (>= n_prims: long primitives are split)
     float4* d_nodes4 = nullptr;      // 4-wide collapse, 8 x float4 per node
     uint32_t n_nodes4 = 0, depth4 = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};

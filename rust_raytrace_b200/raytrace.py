@@ -223,7 +223,7 @@ class Scene:
     def download_bvh(self):
         inf = self.info()
         nodes = np.zeros((inf.n_nodes, 8), np.float32)
-        order = np.zeros(inf.n_prims, np.uint32)
+        order = np.zeros(inf.n_refs, np.uint32)
         check(lib().rtb_scene_download_bvh(self._h, nodes.ctypes.data, order.ctypes.data), "rtb_scene_download_bvh")
         return nodes, order
 

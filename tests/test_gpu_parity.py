@@ -236,7 +236,7 @@ def test_teapot_field_1m_triangles(R, O):
     inf = s.info()
     assert inf.n_tris == 985921 and inf.n_prims == 985920 and inf.max_leaf <= 4
     _, order = s.download_bvh()
-    assert np.array_equal(np.sort(order), np.arange(1, 985921, dtype=np.uint32))
+    assert inf.n_refs >= inf.n_prims and np.array_equal(np.unique(order), np.arange(1, 985921, dtype=np.uint32))
     osc = O.Scene(s.tris.view(O.TRI_DTYPE), O.ACCEL_BVH)
     v, ov = R.main_viewport(960, 540, 5, 1), O.main_viewport(960, 540, 5, 1)
     assert_bit_exact(gpu_render(R, s, v, seed=3), osc.render(ov, seed=3), "teapot field")
@@ -248,7 +248,7 @@ def test_stats_variant_and_bvh_shape(R, scenes):
     inf = s.info()
     assert inf.n_tris == 6721 and inf.n_prims == 6720 and inf.max_leaf <= 4 and inf.tree_height < 62
     nodes, order = s.download_bvh()
-    assert sorted(order.tolist()) == list(range(1, 6721))
+    assert inf.n_refs >= 6720 and len(order) == inf.n_refs and sorted(set(order.tolist())) == list(range(1, 6721))
     a = gpu_render(R, s, R.main_viewport(640, 360, 5, 1), seed=1)
     b = gpu_render(R, s, R.main_viewport(640, 360, 5, 1), seed=1, stats=True)
     assert np.array_equal(bits(a[0]), bits(b[0]))
