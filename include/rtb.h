@@ -148,6 +148,39 @@ const char* rtb_last_error(void);
  * the reference and are culled here too.  root_len2 <= 0 disables the cull. */
 int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
                      rtb_scene** out);
+
+/* Scene assembly on the GPU (the step in front of the path: obj_parser::parse_obj's per-face work,
+ * obj_parser.rs:47-73, and make_triangle, raytrace.rs:340-383, as one kernel).  One indexed mesh
+ * (verts: 3 f32 per vertex; faces: three 1-based vertex indices per face, as in an OBJ file) is instantiated
+ * n_inst times: point = change_basis(v * scale, transform) + offset (rows of `transform` as create_transform
+ * returns them, raytrace.rs:1320-1341), every face becomes one `Triangle` with the instance's surface. */
+typedef struct RtbMeshInstance {
+    float transform_rows[9];
+    float offset[3];
+    float scale;
+    float edge_thickness;
+    uint32_t kind;            /* RTB_SOLID / RTB_MATTE / RTB_REFLECTIVE */
+    float color[3];
+    float alpha;
+    float scattering;
+} RtbMeshInstance;
+
+/* Like rtb_scene_create for the triangle array [dummy, instance 0 faces, instance 1 faces, ..., extra[0..n_extra)]
+ * (main.rs:116-152: dummy, parse_obj(teapot), make_disk, make_disk), without that array ever existing on the host:
+ * the `Triangle` records are computed on every selected GPU, bit-identical to the reference's make_triangle.
+ * RTB_ERR_INVALID where the reference would panic (degenerate face, raytrace.rs:357) or a face index is out of range. */
+int rtb_scene_create_instanced(const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces,
+                               const RtbMeshInstance* inst, uint32_t n_inst, const RtbTriangle* extra,
+                               uint32_t n_extra, const float root_orig[3], float root_len2, rtb_scene** out);
+/* The assembly kernel alone: writes the nfaces*n_inst records to the HOST array `out` (inspection, parity tests, or a
+ * host that wants its Vec<Triangle> computed at GPU speed). */
+int rtb_assemble_triangles(const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces,
+                           const RtbMeshInstance* inst, uint32_t n_inst, RtbTriangle* out);
+/* The root-cube cull kernel alone (box_contains_polygon, raytrace.rs:753-779, per triangle; triangle 0 never
+ * passes): ascending indices of the kept triangles to keep_out (nullable, capacity n), their number to *n_keep. */
+int rtb_cull_triangles(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
+                       uint32_t* keep_out, uint32_t* n_keep);
+
 int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* out);
 void rtb_scene_destroy(rtb_scene* s);
 /* Debug/inspection: copy the BVH of GPU 0 back (nodes: n_nodes*8 floats; prim_order: n_refs u32

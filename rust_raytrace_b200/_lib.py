@@ -96,10 +96,17 @@ class RtbSurface(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("color", C.c_float * 3), ("alpha", C.c_float), ("scattering", C.c_float)]
 
 
+class RtbMeshInstance(C.Structure):
+    _fields_ = [("transform_rows", C.c_float * 9), ("offset", C.c_float * 3), ("scale", C.c_float),
+                ("edge_thickness", C.c_float), ("kind", C.c_uint32), ("color", C.c_float * 3), ("alpha", C.c_float),
+                ("scattering", C.c_float)]
+
+
 # Every symbol include/rtb.h and include/rtb_host.h declare (checked by tests/test_abi.py).
 RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
-    "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render", "rtb_render_device", "rtb_render_progressive",
+    "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_scene_create_instanced", "rtb_assemble_triangles",
+    "rtb_cull_triangles", "rtb_render", "rtb_render_device", "rtb_render_progressive",
     "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
 ]
 RTBH_SYMBOLS = [
@@ -136,6 +143,9 @@ def lib():
     L.rtb_device_count.argtypes = []
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_scene_create.argtypes = [vp, u32, f, C.c_float, C.POINTER(vp)]
+    L.rtb_scene_create_instanced.argtypes = [vp, u32, vp, u32, vp, u32, vp, u32, f, C.c_float, C.POINTER(vp)]
+    L.rtb_assemble_triangles.argtypes = [vp, u32, vp, u32, vp, u32, vp]
+    L.rtb_cull_triangles.argtypes = [vp, u32, f, C.c_float, vp, C.POINTER(u32)]
     L.rtb_scene_info.argtypes = [vp, C.POINTER(RtbSceneInfo)]
     L.rtb_scene_destroy.argtypes = [vp]
     L.rtb_scene_destroy.restype = None

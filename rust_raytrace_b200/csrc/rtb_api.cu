@@ -314,30 +314,65 @@ void rtb_shutdown(void) {
     g_workers.clear();
 }
 
-int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
-                     rtb_scene** out) {
-    if (!out) return fail(RTB_ERR_INVALID, "out is NULL");
+namespace {
+
+// Where a scene's triangle array comes from: finished `Triangle`s of the host (rtb_scene_create), or one mesh + per-
+// instance records assembled on the device (rtb_scene_create_instanced) followed by ready-made extras.
+struct TriSource {
+    const RtbTriangle* tris = nullptr; uint32_t n = 0;            // host triangles (index 0 = dummy)
+    const float* verts = nullptr; uint32_t nverts = 0;            // instanced mesh
+    const uint32_t* faces = nullptr; uint32_t nfaces = 0;
+    const RtbMeshInstance* inst = nullptr; uint32_t n_inst = 0;
+    const RtbTriangle* extra = nullptr; uint32_t n_extra = 0;
+    bool instanced = false;
+    uint32_t total() const { return instanced ? 1u + nfaces * n_inst + n_extra : n; }
+};
+
+cudaError_t upload(void** d, const void* h, size_t bytes, cudaStream_t st) {
+    cudaError_t e = cudaMalloc(d, bytes ? bytes : 4);
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+// Fills d_tris[0 .. src.total()) on the current device.
+int produce_triangles(const TriSource& src, RtbTriangle* d_tris, cudaStream_t st) {
+    if (!src.instanced) {
+        if (src.n) RTB_CUDA(cudaMemcpyAsync(d_tris, src.tris, sizeof(RtbTriangle) * src.n, cudaMemcpyHostToDevice, st));
+        RTB_CUDA(cudaStreamSynchronize(st));
+        return RTB_OK;
+    }
+    const RtbTriangle dummy = raytrace::make_dummy_triangle();     // triangle 0 (main.rs:117), never tested
+    RTB_CUDA(cudaMemcpyAsync(d_tris, &dummy, sizeof dummy, cudaMemcpyHostToDevice, st));
+    float* d_verts = nullptr; uint32_t* d_faces = nullptr; RtbMeshInstance* d_inst = nullptr;
+    auto cleanup = [&] { cudaFree(d_verts); cudaFree(d_faces); cudaFree(d_inst); };
+    cudaError_t e = upload((void**)&d_verts, src.verts, sizeof(float) * 3 * (size_t)src.nverts, st);
+    if (e == cudaSuccess) e = upload((void**)&d_faces, src.faces, sizeof(uint32_t) * 3 * (size_t)src.nfaces, st);
+    if (e == cudaSuccess) e = upload((void**)&d_inst, src.inst, sizeof(RtbMeshInstance) * (size_t)src.n_inst, st);
+    if (e != cudaSuccess) { cleanup(); return rtb_cuda_fail(e, "mesh upload", __FILE__, __LINE__); }
+    uint32_t bad = 0xffffffffu;
+    int rc = rtb_launch_assemble(d_verts, src.nverts, d_faces, src.nfaces, d_inst, src.n_inst, d_tris + 1, st, &bad);
+    cleanup();
+    if (rc != RTB_OK) return rc;
+    if (bad != 0xffffffffu)
+        return fail(RTB_ERR_INVALID, "make_triangle fails for face " + std::to_string(bad % src.nfaces) + " of instance " +
+                                         std::to_string(bad / src.nfaces) +
+                                         " (vertex index out of range, or a degenerate triangle: the reference panics, raytrace.rs:357)");
+    if (src.n_extra)
+        RTB_CUDA(cudaMemcpyAsync(d_tris + 1 + (size_t)src.nfaces * src.n_inst, src.extra, sizeof(RtbTriangle) * src.n_extra,
+                                 cudaMemcpyHostToDevice, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    return RTB_OK;
+}
+
+int scene_create_common(const TriSource& src, const float root_orig[3], float root_len2, rtb_scene** out) {
     *out = nullptr;
-    if (n > 0 && !tris) return fail(RTB_ERR_INVALID, "tris is NULL");
     int rc = ensure_init();
     if (rc != RTB_OK) return rc;
-
-    // Root-cube cull (raytrace.rs:795-805): triangle 0 is never in the tree (:791).
-    std::vector<uint32_t> keep;
-    keep.reserve(n);
-    for (uint32_t i = 1; i < n; ++i) {
-        if (root_len2 > 0.f && root_orig) {
-            const raytrace::Point c = raytrace::make_vec(root_orig[0], root_orig[1], root_orig[2]);
-            if (!raytrace::box_contains_polygon(c, root_len2, tris[i])) continue;
-        }
-        keep.push_back(i);
-    }
-    const uint32_t n_prims = (uint32_t)keep.size();
+    const uint32_t n = src.total();
 
     rtb_scene* s = new rtb_scene();
     std::memset(&s->info, 0, sizeof s->info);
     s->info.n_tris = n;
-    s->info.n_prims = n_prims;
     s->info.n_gpus = (uint32_t)g_devices.size();
     s->gpu.resize(g_devices.size());
 
@@ -358,19 +393,19 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
         if ((e = cudaMalloc(&g.d_counters, sizeof(TraceCounters))) != cudaSuccess)
             return bail(rtb_cuda_fail(e, "cudaMalloc(counters)", __FILE__, __LINE__));
 
+        // triangles on the device (H2D, or assembled there), then the root-cube cull (raytrace.rs:795-805; triangle 0
+        // is never in the tree, :791) as a kernel + ordered compaction
         const double t0 = now_ms();
         RtbTriangle* d_tris = nullptr;
         uint32_t* d_keep = nullptr;
+        uint32_t n_prims = 0;
         if ((e = cudaMalloc(&d_tris, sizeof(RtbTriangle) * (n ? n : 1))) != cudaSuccess)
             return bail(rtb_cuda_fail(e, "cudaMalloc(tris)", __FILE__, __LINE__));
-        if ((e = cudaMalloc(&d_keep, sizeof(uint32_t) * (n_prims ? n_prims : 1))) != cudaSuccess) {
-            cudaFree(d_tris);
-            return bail(rtb_cuda_fail(e, "cudaMalloc(keep)", __FILE__, __LINE__));
-        }
-        cudaMemcpyAsync(d_tris, tris, sizeof(RtbTriangle) * n, cudaMemcpyHostToDevice, g.stream);
-        cudaMemcpyAsync(d_keep, keep.data(), sizeof(uint32_t) * n_prims, cudaMemcpyHostToDevice, g.stream);
-        cudaStreamSynchronize(g.stream);
+        rc = produce_triangles(src, d_tris, g.stream);
+        if (rc == RTB_OK) rc = rtb_launch_cull(d_tris, n, root_orig, root_len2, g.stream, &d_keep, &n_prims);
+        if (rc != RTB_OK) { cudaFree(d_tris); cudaFree(d_keep); return bail(rc); }
         const double t1 = now_ms();
+        if (gi == 0) s->info.n_prims = n_prims;
 
         BuildResult br;
         rc = rtb_build_lbvh(d_tris, d_keep, n_prims, g.stream, &br);
@@ -393,6 +428,85 @@ int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[
     }
     *out = s;
     return RTB_OK;
+}
+
+}  // namespace
+
+int rtb_scene_create(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
+                     rtb_scene** out) {
+    if (!out) return fail(RTB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n > 0 && !tris) return fail(RTB_ERR_INVALID, "tris is NULL");
+    TriSource src;
+    src.tris = tris; src.n = n;
+    return scene_create_common(src, root_orig, root_len2, out);
+}
+
+namespace {
+int check_mesh_args(const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces,
+                    const RtbMeshInstance* inst, uint32_t n_inst) {
+    if ((nverts && !verts) || (nfaces && !faces) || (n_inst && !inst)) return fail(RTB_ERR_INVALID, "NULL mesh argument");
+    if ((uint64_t)nfaces * n_inst > 0x7fffff00ull) return fail(RTB_ERR_INVALID, "too many triangles");
+    return RTB_OK;
+}
+}  // namespace
+
+int rtb_scene_create_instanced(const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces,
+                               const RtbMeshInstance* inst, uint32_t n_inst, const RtbTriangle* extra,
+                               uint32_t n_extra, const float root_orig[3], float root_len2, rtb_scene** out) {
+    if (!out) return fail(RTB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_mesh_args(verts, nverts, faces, nfaces, inst, n_inst);
+    if (rc != RTB_OK) return rc;
+    if (n_extra && !extra) return fail(RTB_ERR_INVALID, "extra is NULL");
+    TriSource src;
+    src.instanced = true;
+    src.verts = verts; src.nverts = nverts; src.faces = faces; src.nfaces = nfaces;
+    src.inst = inst; src.n_inst = n_inst; src.extra = extra; src.n_extra = n_extra;
+    return scene_create_common(src, root_orig, root_len2, out);
+}
+
+int rtb_assemble_triangles(const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces,
+                           const RtbMeshInstance* inst, uint32_t n_inst, RtbTriangle* out) {
+    int rc = check_mesh_args(verts, nverts, faces, nfaces, inst, n_inst);
+    if (rc != RTB_OK) return rc;
+    if (!out) return fail(RTB_ERR_INVALID, "out is NULL");
+    rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(g_devices[0]));
+    TriSource src;
+    src.instanced = true;
+    src.verts = verts; src.nverts = nverts; src.faces = faces; src.nfaces = nfaces; src.inst = inst; src.n_inst = n_inst;
+    const uint32_t n = src.total();
+    RtbTriangle* d_tris = nullptr;
+    RTB_CUDA(cudaMalloc(&d_tris, sizeof(RtbTriangle) * n));
+    rc = produce_triangles(src, d_tris, nullptr);
+    if (rc == RTB_OK) {
+        cudaError_t e = cudaMemcpy(out, d_tris + 1, sizeof(RtbTriangle) * (n - 1), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = rtb_cuda_fail(e, "cudaMemcpy(triangles)", __FILE__, __LINE__);
+    }
+    cudaFree(d_tris);
+    return rc;
+}
+
+int rtb_cull_triangles(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
+                       uint32_t* keep_out, uint32_t* n_keep) {
+    if ((n && !tris) || !n_keep) return fail(RTB_ERR_INVALID, "NULL argument");
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaSetDevice(g_devices[0]));
+    RtbTriangle* d_tris = nullptr;
+    RTB_CUDA(cudaMalloc(&d_tris, sizeof(RtbTriangle) * (n ? n : 1)));
+    cudaError_t e = n ? cudaMemcpy(d_tris, tris, sizeof(RtbTriangle) * n, cudaMemcpyHostToDevice) : cudaSuccess;
+    uint32_t* d_keep = nullptr;
+    rc = e == cudaSuccess ? rtb_launch_cull(d_tris, n, root_orig, root_len2, nullptr, &d_keep, n_keep)
+                          : rtb_cuda_fail(e, "cudaMemcpy(triangles)", __FILE__, __LINE__);
+    if (rc == RTB_OK && keep_out && *n_keep) {
+        e = cudaMemcpy(keep_out, d_keep, sizeof(uint32_t) * *n_keep, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = rtb_cuda_fail(e, "cudaMemcpy(keep)", __FILE__, __LINE__);
+    }
+    cudaFree(d_tris); cudaFree(d_keep);
+    return rc;
 }
 
 int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* out) {

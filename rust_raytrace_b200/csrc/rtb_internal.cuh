@@ -153,6 +153,14 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
 // Self-test of the hand-written radix sort / scan (rtb_sort.cuh) against the host.
 int rtb_sort_selftest(uint32_t n, int key_bits, uint64_t seed);
 
+// ---- implemented in rtb_scene.cu ----------------------------------------------
+// Scene assembly on the device: mesh instances -> `Triangle` records (make_triangle), root-cube cull + compaction.
+int rtb_launch_assemble(const float* d_verts, uint32_t nverts, const uint32_t* d_faces, uint32_t nfaces,
+                        const RtbMeshInstance* d_inst, uint32_t n_inst, RtbTriangle* d_out, cudaStream_t stream,
+                        uint32_t* h_first_bad);
+int rtb_launch_cull(const RtbTriangle* d_tris, uint32_t n, const float root_orig[3], float root_len2,
+                    cudaStream_t stream, uint32_t** d_keep_out, uint32_t* n_keep);
+
 // ---- implemented in rtb_trace.cu ----------------------------------------------
 // Launches the trace kernel for the tile rows owned by (tile_rank, tile_world).
 int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint32_t* d_prim, float* d_t,

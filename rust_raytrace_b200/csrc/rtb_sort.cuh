@@ -36,7 +36,7 @@ __device__ __forceinline__ void warp_histogram(const unsigned long long* __restr
 }
 
 // pass kernel 1: per-block digit histogram -> hist[d * n_blocks + block]
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
+static __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
                                                        uint32_t n_blocks, uint32_t* __restrict__ hist) {
     __shared__ uint32_t wh[RS_WARPS][RS_DIGITS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned long long
 }
 
 // pass kernel 3: stable scatter.  offs = exclusive scan of hist (global start of (digit, block)).
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned long long* __restrict__ keys_in,
+static __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned long long* __restrict__ keys_in,
                                                           const uint32_t* __restrict__ vals_in, uint32_t n, int shift,
                                                           uint32_t n_blocks, const uint32_t* __restrict__ offs,
                                                           unsigned long long* __restrict__ keys_out,

@@ -23,8 +23,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (RTB_FLAG_STATS, RTB_FLAG_SUM_ONLY, RTB_MATTE, RTB_REFLECTIVE, RTB_SOLID, TRI_DTYPE, RtbSceneInfo,
-                   RtbStats, RtbSurface, RtbView, check, lib)
+from ._lib import (RTB_FLAG_STATS, RTB_FLAG_SUM_ONLY, RTB_MATTE, RTB_REFLECTIVE, RTB_SOLID, TRI_DTYPE, RtbMeshInstance,
+                   RtbSceneInfo, RtbStats, RtbSurface, RtbView, check, lib)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 TEAPOT_MESH = os.path.join(_PKG, "data", "teapot_mesh.bin")
@@ -240,6 +240,82 @@ class Scene:
 
 
 # ---------------------------------------------------------------------------
+# Scene assembly on the GPU: parse_obj's per-face work + make_triangle as a kernel
+# ---------------------------------------------------------------------------
+def mesh_instance(offset, scale, transform, surface: SurfaceKind, edge_thickness) -> RtbMeshInstance:
+    """One `parse_obj(path, offset, scale, transform, surface, edge_thickness)` call (obj_parser.rs:47-52) minus the file."""
+    c = surface._c()
+    m = RtbMeshInstance()
+    m.transform_rows[:] = [float(x) for x in np.asarray(transform, np.float32).reshape(9)]
+    m.offset[:] = [float(x) for x in offset]
+    m.scale, m.edge_thickness = float(scale), float(edge_thickness)
+    m.kind, m.alpha, m.scattering = c.kind, c.alpha, c.scattering
+    m.color[:] = c.color[:]
+    return m
+
+
+def _inst_array(instances):
+    arr = (RtbMeshInstance * max(len(instances), 1))()
+    for k, m in enumerate(instances):
+        arr[k] = m
+    return arr
+
+
+def assemble_triangles(verts, faces, instances):
+    """`Triangle` records of every (instance, face), computed on the GPU (rtb_assemble_triangles)."""
+    verts = np.ascontiguousarray(verts, np.float32)
+    faces = np.ascontiguousarray(faces, np.uint32)
+    out = np.zeros(len(faces) * len(instances), TRI_DTYPE)
+    arr = _inst_array(instances)       # keep the ctypes array alive across the call
+    check(lib().rtb_assemble_triangles(verts.ctypes.data, len(verts), faces.ctypes.data, len(faces),
+                                       C.addressof(arr), len(instances), out.ctypes.data), "rtb_assemble_triangles")
+    return out
+
+
+def cull_triangles(tris, boxes):
+    """Indices of the triangles the octree root cube keeps (box_contains_polygon, raytrace.rs:753-779), on the GPU."""
+    tris = np.ascontiguousarray(tris, TRI_DTYPE)
+    keep = np.zeros(len(tris), np.uint32)
+    n = C.c_uint32()
+    ro, rl = (None, 0.0) if boxes is None else (_f(boxes[0]), float(boxes[1]))
+    check(lib().rtb_cull_triangles(tris.ctypes.data, len(tris), ro, rl, keep.ctypes.data, C.byref(n)), "rtb_cull_triangles")
+    return keep[:n.value]
+
+
+class InstancedScene(Scene):
+    """A scene given as one indexed mesh + instances (+ ready-made extra triangles): the `Triangle` array
+    [dummy, instance 0, instance 1, ..., extra] is built on the GPU and never exists on the host unless `.tris` is read."""
+
+    def __init__(self, verts, faces, instances, extra=None, boxes=((0.0, 0.0, 20.1), 20.0)):
+        self.verts = np.ascontiguousarray(verts, np.float32)
+        self.faces = np.ascontiguousarray(faces, np.uint32)
+        self.instances = list(instances)
+        self.extra = np.zeros(0, TRI_DTYPE) if extra is None else np.ascontiguousarray(extra, TRI_DTYPE)
+        self.boxes = boxes
+        self._h = None
+        self._tris = None
+
+    @property
+    def tris(self):
+        if self._tris is None:
+            self._tris = np.concatenate([make_dummy_triangle(), assemble_triangles(self.verts, self.faces, self.instances),
+                                         self.extra])
+        return self._tris
+
+    def upload(self):
+        if self._h is None:
+            h = C.c_void_p()
+            ro, rl = (None, 0.0) if self.boxes is None else (_f(self.boxes[0]), float(self.boxes[1]))
+            arr = _inst_array(self.instances)      # keep the ctypes array alive across the call
+            check(lib().rtb_scene_create_instanced(self.verts.ctypes.data, len(self.verts), self.faces.ctypes.data,
+                                                   len(self.faces), C.addressof(arr),
+                                                   len(self.instances), self.extra.ctypes.data if len(self.extra) else None,
+                                                   len(self.extra), ro, rl, C.byref(h)), "rtb_scene_create_instanced")
+            self._h = h
+        return self._h
+
+
+# ---------------------------------------------------------------------------
 # progress.rs:9-185 (the part a caster must feed)
 # ---------------------------------------------------------------------------
 @dataclass
@@ -359,7 +435,7 @@ def quantize_rgb8(data):
 # ---------------------------------------------------------------------------
 # The reference's benchmark scene and camera (raytrace/src/main.rs:116-173)
 # ---------------------------------------------------------------------------
-def main_scene(deterministic=False, mesh_path=TEAPOT_MESH) -> Scene:
+def main_scene(deterministic=False, mesh_path=TEAPOT_MESH, instanced=False) -> Scene:
     """Scene of main.rs:116-164.  deterministic=True uses the materials of the deterministic
     parity mode: teapot Solid(252,119,0) (the commented line main.rs:123), disks Reflective with
     scattering 0, disk sides Solid."""
@@ -374,6 +450,12 @@ def main_scene(deterministic=False, mesh_path=TEAPOT_MESH) -> Scene:
         d2 = SurfaceKind.Reflective(0.002, grey, 0.7)
         side = SurfaceKind.Matte(dark, 0.2)
     tf = create_transform(unit([0.0, 0.3, 1.0]), to_radians(270.0))
+    if instanced:      # the teapot's `Triangle`s are computed on the GPU (InstancedScene)
+        verts, faces = obj_parser.load_mesh_bin(mesh_path)
+        disks = np.concatenate([make_disk([4.0, 4.0, 7.0], unit([-0.3, -0.55, -0.5]), 2.0, 0.1, 50, d1, side, -1.0),
+                                make_disk([4.0, -3.0, 5.0], unit([-0.5, 2.0, -0.5]), 1.0, 0.04, 50, d2, side, -1.0)])
+        return InstancedScene(verts, faces, [mesh_instance([0.0, 0.5, 5.0], 1.0, tf, teapot, 0.05)], disks,
+                              boxes=((0.0, 0.0, 20.1), 20.0))
     if mesh_path.endswith(".obj"):
         pot = obj_parser.parse_obj(mesh_path, [0.0, 0.5, 5.0], 1.0, tf, teapot, 0.05)
     else:
@@ -388,7 +470,7 @@ def main_scene(deterministic=False, mesh_path=TEAPOT_MESH) -> Scene:
     return Scene(tris, boxes=((0.0, 0.0, 20.1), 20.0))
 
 
-def teapot_field_scene(nz=12, ny=13, seed=1, surface=None, scale=0.3, mesh_path=TEAPOT_MESH) -> Scene:
+def teapot_field_scene(nz=12, ny=13, seed=1, surface=None, scale=0.3, mesh_path=TEAPOT_MESH, instanced=False) -> Scene:
     """BASELINE config 4: nz x ny instanced teapots (12 x 13 = 156 -> 985,920 triangles + the dummy) standing on a
     grid that recedes from main.rs's camera, every instance with its own roll angle from an LCG (fixed seed) and
     mirror-like `Reflective{scattering: 0}` surfaces so that bounce rays are incoherent.  All instances lie inside
@@ -397,6 +479,7 @@ def teapot_field_scene(nz=12, ny=13, seed=1, surface=None, scale=0.3, mesh_path=
         surface = SurfaceKind.Reflective(0.0, make_color((252, 119, 0)), 0.5)
     verts, faces = obj_parser.load_mesh_bin(mesh_path)
     parts = [make_dummy_triangle()]
+    insts = []
     state = int(seed) & 0xFFFFFFFF
     for iz in range(nz):
         for iy in range(ny):
@@ -404,7 +487,12 @@ def teapot_field_scene(nz=12, ny=13, seed=1, surface=None, scale=0.3, mesh_path=
             roll = 270.0 + 360.0 * (state >> 8) / float(1 << 24)
             tf = create_transform(unit([0.0, 0.3, 1.0]), to_radians(roll))
             off = [-1.2, (iy - (ny - 1) / 2.0) * 2.2, 3.0 + 2.0 * iz]
-            parts.append(obj_parser.mesh_to_triangles(verts, faces, off, scale, tf, surface, 0.05))
+            if instanced:
+                insts.append(mesh_instance(off, scale, tf, surface, 0.05))
+            else:
+                parts.append(obj_parser.mesh_to_triangles(verts, faces, off, scale, tf, surface, 0.05))
+    if instanced:      # 76 KB of mesh + 156 instance records instead of 138 MB of finished triangles
+        return InstancedScene(verts, faces, insts, None, boxes=((0.0, 0.0, 20.1), 20.0))
     return Scene(np.concatenate(parts), boxes=((0.0, 0.0, 20.1), 20.0))
 
 

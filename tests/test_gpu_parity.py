@@ -329,3 +329,84 @@ def test_progressive_psnr(R, O, scenes):
     mse = float(np.mean((np.clip(data[..., :3], 0, 1) - np.clip(ref, 0, 1)) ** 2))
     psnr = 10 * np.log10(1.0 / mse)
     assert psnr >= 40.0, psnr
+
+
+# ---------------------------------------------------------------------------
+# scene assembly on the GPU: make_triangle / parse_obj's transform / root-cube cull as kernels
+# ---------------------------------------------------------------------------
+def test_gpu_make_triangle_bit_exact(R, O, teapot_mesh):
+    """rtb_assemble_triangles (k_assemble) against the oracle's make_triangle (raytrace.rs:340-383) and the host mirror:
+    every one of the 35 fields of every record, bit for bit — main.rs's teapot and rolled / scaled / shifted instances."""
+    from rust_raytrace_b200 import raytrace as rt
+    verts, faces = teapot_mesh
+    cases = [([0.0, 0.5, 5.0], 1.0, 270.0, R.SurfaceKind.Matte(R.make_color((252, 119, 0)), 0.2), 0.05),
+             ([-1.2, 3.3, 9.0], 0.3, 301.7, R.SurfaceKind.Reflective(0.002, R.make_color((1, 2, 3)), 0.5), -1.0),
+             ([7.0, -2.0, 30.0], 2.5, 12.0, R.SurfaceKind.Solid(R.make_color((9, 8, 7))), 0.0)]
+    insts, want, want_o = [], [], []
+    for off, scale, roll, surf, edge in cases:
+        tf = R.create_transform(R.unit([0.0, 0.3, 1.0]), R.to_radians(roll))
+        insts.append(rt.mesh_instance(off, scale, tf, surf, edge))
+        want.append(R.obj_parser.mesh_to_triangles(verts, faces, off, scale, tf, surf, edge))
+        otf = O.create_transform(O.unit([0.0, 0.3, 1.0]), O.to_radians(roll))
+        c = surf._c()
+        want_o.append(O.mesh_to_triangles(verts, faces, off, scale, otf, O.Surface(c.kind, list(c.color), c.alpha, c.scattering), edge))
+    got = rt.assemble_triangles(verts, faces, insts)
+    assert len(got) == 3 * len(faces)
+    assert got.tobytes() == np.concatenate(want_o).tobytes(), "GPU make_triangle differs from the oracle"
+    assert got.tobytes() == np.concatenate(want).tobytes()
+
+
+def test_gpu_make_triangle_rejects_what_the_reference_panics_on(R):
+    from rust_raytrace_b200 import raytrace as rt
+    from rust_raytrace_b200._lib import RtbError
+    tf = R.create_transform(R.unit([0.0, 0.0, 1.0]), 0.0)
+    inst = [rt.mesh_instance([0, 0, 5], 1.0, tf, R.SurfaceKind.Solid([1, 1, 1]), 0.0)]
+    good = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 1], [2, 2, 2]], np.float32)
+    assert len(rt.assemble_triangles(good, np.array([[1, 2, 3]], np.uint32), inst)) == 1
+    for faces in ([[1, 4, 5]], [[1, 2, 3], [1, 2, 9]], [[0, 1, 2]]):      # collinear corners; index out of range; 0-based
+        with pytest.raises(RtbError) as e:
+            rt.assemble_triangles(good, np.array(faces, np.uint32), inst)
+        assert e.value.code == -3
+
+
+def test_gpu_root_cube_cull_equals_host(R, scenes):
+    """k_cull_flags + compaction against box_contains_polygon of the host mirror (raytrace.rs:753-779) on cubes that
+    cut through the scene, so that all three outcomes (corner inside, face crossing, outside) occur."""
+    from rust_raytrace_b200 import _lib, raytrace as rt
+    L = _lib.lib()
+    tris = scenes[False][0].tris
+    for boxes in (((0.0, 0.0, 20.1), 20.0), ((0.0, 0.5, 5.0), 1.0), ((4.0, 4.0, 7.0), 0.7), ((2.0, 0.0, 4.0), 0.3), ((50.0, 0.0, 0.0), 1.0)):
+        f3 = (C.c_float * 3)(*boxes[0])
+        want = [i for i in range(1, len(tris)) if L.rtbh_box_contains_polygon(f3, boxes[1], tris[i:i + 1].ctypes.data) == 1]
+        got = rt.cull_triangles(tris, boxes)
+        assert got.tolist() == want, boxes
+    assert rt.cull_triangles(tris, None).tolist() == list(range(1, len(tris)))
+    assert 0 < len(rt.cull_triangles(tris, ((0.0, 0.5, 5.0), 1.0))) < 6720
+
+
+def test_instanced_scene_equals_uploaded_scene(R, scenes):
+    """rtb_scene_create_instanced (triangles computed on the GPU) must give the same tree and the same frame as
+    rtb_scene_create with the host-made triangle array."""
+    s_host = scenes[False][0]
+    s_inst = R.main_scene(deterministic=False, instanced=True)
+    a, b = s_host.info(), s_inst.info()
+    assert (a.n_tris, a.n_prims, a.n_refs, a.n_nodes, a.n_leaves) == (b.n_tris, b.n_prims, b.n_refs, b.n_nodes, b.n_leaves)
+    assert s_inst.tris.tobytes() == s_host.tris.tobytes()
+    v = R.main_viewport(640, 360, 5, 1)
+    x, y = gpu_render(R, s_host, v, seed=2), gpu_render(R, s_inst, v, seed=2)
+    assert np.array_equal(x[1], y[1]) and np.array_equal(bits(x[2]), bits(y[2])) and np.array_equal(bits(x[0]), bits(y[0]))
+    assert x[3].total_rays == y[3].total_rays
+    s_inst.release()
+
+
+def test_instanced_teapot_field_1m(R):
+    """BASELINE config 4 built from 76 KB of mesh + 156 instance records: same counts and the same frame as the
+    138 MB host-array upload (which test_teapot_field_1m_triangles compares with the oracle)."""
+    s_inst, s_host = R.teapot_field_scene(instanced=True), R.teapot_field_scene()
+    a, b = s_host.info(), s_inst.info()
+    assert (a.n_tris, a.n_prims, a.n_refs, a.n_nodes) == (b.n_tris, b.n_prims, b.n_refs, b.n_nodes) and b.n_prims == 985920
+    v = R.main_viewport(480, 270, 5, 1)
+    x, y = gpu_render(R, s_host, v, seed=3), gpu_render(R, s_inst, v, seed=3)
+    assert np.array_equal(x[1], y[1]) and np.array_equal(bits(x[0]), bits(y[0]))
+    s_host.release()
+    s_inst.release()

@@ -36,15 +36,17 @@ def test_struct_sizes_match_the_header(R, tmp_path):
 #include "rtb.h"
 #include "rtb_host.h"
 int main(void) {
-    printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(RtbTriangle), sizeof(RtbView), sizeof(RtbStats), sizeof(RtbSceneInfo),
-           sizeof(RtbSurface), offsetof(RtbView, seed), offsetof(RtbStats, ms_stage), offsetof(RtbSceneInfo, ms_upload));
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(RtbTriangle), sizeof(RtbView), sizeof(RtbStats), sizeof(RtbSceneInfo),
+           sizeof(RtbSurface), offsetof(RtbView, seed), offsetof(RtbStats, ms_stage), offsetof(RtbSceneInfo, ms_upload),
+           sizeof(RtbMeshInstance), offsetof(RtbMeshInstance, kind), offsetof(RtbSceneInfo, n_refs));
     return 0;
 }''')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [_lib.TRI_DTYPE.itemsize, C.sizeof(_lib.RtbView), C.sizeof(_lib.RtbStats), C.sizeof(_lib.RtbSceneInfo),
-            C.sizeof(_lib.RtbSurface), _lib.RtbView.seed.offset, _lib.RtbStats.ms_stage.offset, _lib.RtbSceneInfo.ms_upload.offset]
+            C.sizeof(_lib.RtbSurface), _lib.RtbView.seed.offset, _lib.RtbStats.ms_stage.offset, _lib.RtbSceneInfo.ms_upload.offset,
+            C.sizeof(_lib.RtbMeshInstance), _lib.RtbMeshInstance.kind.offset, _lib.RtbSceneInfo.n_refs.offset]
     assert got == want, (got, want)
     assert got[0] == 140 and got[1] == 88
 
@@ -145,3 +147,10 @@ def test_gpu_path_fails_loudly_without_a_device(R):
     with pytest.raises(RtbError) as e:
         R.B200RayCaster().walk_rays(v, R.main_scene(), R.new_image(v), threads=1)
     assert e.value.code == -1
+    # the scene-assembly entry points have no host fallback either
+    from rust_raytrace_b200 import raytrace as rt
+    sc = R.main_scene(instanced=True)
+    for call in (sc.upload, lambda: sc.tris, lambda: rt.cull_triangles(R.main_scene().tris, ((0.0, 0.0, 20.1), 20.0))):
+        with pytest.raises(RtbError) as e:
+            call()
+        assert e.value.code == -1
