@@ -196,6 +196,11 @@ int rtb_scene_download_bvh(const rtb_scene* s, float* nodes, uint32_t* prim_orde
 int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* prim_out, float* t_out,
                RtbStats* stats);
 
+/* The same frame delivered the way main.rs consumes it (walk_rays then write_png, main.rs:191-227): quantised on the
+ * GPU with write_png's `(c * 255.) as u8` (raytrace.rs:1468-1473) and copied home as width*height*3 bytes, RGB,
+ * row-major — 3 instead of 16 bytes per pixel over PCIe.  rtbh_write_png_rgb8 (rtb_host.h) puts it in a PNG file. */
+int rtb_render_rgb8(rtb_scene* s, const RtbView* view, uint8_t* rgb_out, RtbStats* stats);
+
 /* Render the tile subset `tile_rank` of `tile_world` (tile i belongs to rank i % world) of one frame
  * into DEVICE buffers (full-frame indexing, pixels of other ranks untouched) on GPU slot `gpu`
  * (index into the rtb_init set) and CUDA stream `stream` (a cudaStream_t cast to void*, NULL = the

@@ -17,6 +17,7 @@
  *   rtbh_parse_obj          parse_obj                obj_parser.rs:47-73
  *   rtbh_box_contains_polygon box_contains_polygon   raytrace.rs:753-779
  *   rtbh_write_ppm          write_png (quantiser)    raytrace.rs:1460-1478
+ *   rtbh_write_png[_rgb8]   write_png                raytrace.rs:1460-1478
  */
 #ifndef RTB_HOST_H
 #define RTB_HOST_H
@@ -71,6 +72,13 @@ int rtbh_box_contains_polygon(const float orig[3], float len2, const RtbTriangle
 
 /* Quantise with `(c*255.) as u8` and write a binary PPM (the PNG encoder itself is out of scope). */
 int rtbh_write_ppm(const char* path, uint32_t width, uint32_t height, const float* rgba);
+
+/* write_png (raytrace.rs:1460-1478): 8-bit RGB PNG of the frame.  rtbh_write_png quantises f32 RGBA with the
+ * reference's `(c*255.) as u8`; rtbh_write_png_rgb8 takes pixels that are already quantised (rtb_render_rgb8,
+ * rtb_quantize_rgb8).  The encoder is self-contained (zlib "stored" blocks, CRC-32, Adler-32): the file holds exactly
+ * the bytes the reference's `png` crate would decode to, at no compression. */
+int rtbh_write_png(const char* path, uint32_t width, uint32_t height, const float* rgba);
+int rtbh_write_png_rgb8(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb);
 
 #ifdef __cplusplus
 }

@@ -105,14 +105,14 @@ class RtbMeshInstance(C.Structure):
 # Every symbol include/rtb.h and include/rtb_host.h declare (checked by tests/test_abi.py).
 RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
-    "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_scene_create_instanced", "rtb_assemble_triangles",
+    "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render_rgb8", "rtb_scene_create_instanced", "rtb_assemble_triangles",
     "rtb_cull_triangles", "rtb_render", "rtb_render_device", "rtb_render_progressive",
     "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
 ]
 RTBH_SYMBOLS = [
     "rtbh_make_color", "rtbh_unit", "rtbh_to_radians", "rtbh_make_triangle", "rtbh_make_dummy_triangle",
     "rtbh_make_disk", "rtbh_make_sphere", "rtbh_create_transform", "rtbh_create_viewport", "rtbh_parse_obj",
-    "rtbh_mesh_to_triangles", "rtbh_load_mesh_bin", "rtbh_box_contains_polygon", "rtbh_write_ppm",
+    "rtbh_mesh_to_triangles", "rtbh_load_mesh_bin", "rtbh_box_contains_polygon", "rtbh_write_ppm", "rtbh_write_png", "rtbh_write_png_rgb8",
 ]
 
 
@@ -151,6 +151,7 @@ def lib():
     L.rtb_scene_destroy.restype = None
     L.rtb_scene_download_bvh.argtypes = [vp, vp, vp]
     L.rtb_render.argtypes = [vp, C.POINTER(RtbView), vp, vp, vp, C.POINTER(RtbStats)]
+    L.rtb_render_rgb8.argtypes = [vp, C.POINTER(RtbView), vp, C.POINTER(RtbStats)]
     L.rtb_render_device.argtypes = [vp, C.POINTER(RtbView), C.c_int, u32, u32, vp, vp, vp, vp, C.POINTER(RtbStats)]
     L.rtb_render_progressive.argtypes = [vp, C.POINTER(RtbView), vp, C.POINTER(RtbStats)]
     L.rtb_quantize_rgb8.argtypes = [vp, C.c_uint64, vp]
@@ -181,6 +182,8 @@ def lib():
     L.rtbh_load_mesh_bin.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32), vp, u32, C.POINTER(u32)]
     L.rtbh_box_contains_polygon.argtypes = [f, C.c_float, vp]
     L.rtbh_write_ppm.argtypes = [C.c_char_p, u32, u32, vp]
+    L.rtbh_write_png.argtypes = [C.c_char_p, u32, u32, vp]
+    L.rtbh_write_png_rgb8.argtypes = [C.c_char_p, u32, u32, vp]
     _lib = L
     return L
 

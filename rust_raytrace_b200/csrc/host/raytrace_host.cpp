@@ -3,6 +3,7 @@
 // separate f32 multiplies and adds in the order the reference writes them.
 #include "raytrace_host.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -399,6 +400,84 @@ bool write_ppm(const std::string& path, uint32_t width, uint32_t height, const f
     return ok;
 }
 
+
+// ---- PNG container (write_png, raytrace.rs:1460-1478) ------------------------------
+namespace {
+uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        ready = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+void put_be32(std::vector<uint8_t>& v, uint32_t x) {
+    v.push_back(uint8_t(x >> 24)); v.push_back(uint8_t(x >> 16)); v.push_back(uint8_t(x >> 8)); v.push_back(uint8_t(x));
+}
+bool write_chunk(FILE* f, const char type[4], const std::vector<uint8_t>& body) {
+    std::vector<uint8_t> head;
+    put_be32(head, uint32_t(body.size()));
+    head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32_update(0xffffffffu, head.data() + 4, 4);
+    crc = crc32_update(crc, body.data(), body.size()) ^ 0xffffffffu;
+    std::vector<uint8_t> tail;
+    put_be32(tail, crc);
+    return std::fwrite(head.data(), 1, head.size(), f) == head.size() &&
+           (body.empty() || std::fwrite(body.data(), 1, body.size(), f) == body.size()) &&
+           std::fwrite(tail.data(), 1, 4, f) == 4;
+}
+}  // namespace
+
+bool write_png_rgb8(const std::string& path, uint32_t width, uint32_t height, const uint8_t* rgb) {
+    if (width == 0 || height == 0) return false;
+    // scanlines: filter byte 0 + 3 bytes per pixel
+    const size_t stride = size_t(width) * 3, raw_len = (stride + 1) * height;
+    std::vector<uint8_t> idat;
+    idat.reserve(raw_len + raw_len / 65535 * 5 + 16);
+    idat.push_back(0x78); idat.push_back(0x01);                    // zlib header: deflate, 32 K window, no preset
+    uint32_t a = 1, b = 0;                                         // Adler-32 of the raw scanlines
+    std::vector<uint8_t> raw(raw_len);
+    for (uint32_t y = 0; y < height; ++y) {
+        raw[(stride + 1) * y] = 0;
+        std::memcpy(&raw[(stride + 1) * y + 1], rgb + stride * y, stride);
+    }
+    for (size_t pos = 0; pos < raw_len;) {
+        const size_t n = std::min<size_t>(65535, raw_len - pos);
+        idat.push_back(pos + n == raw_len ? 1 : 0);                // BFINAL, BTYPE = 00 (stored)
+        idat.push_back(uint8_t(n)); idat.push_back(uint8_t(n >> 8));
+        idat.push_back(uint8_t(~n)); idat.push_back(uint8_t((~n) >> 8));
+        idat.insert(idat.end(), raw.begin() + pos, raw.begin() + pos + n);
+        for (size_t i = 0; i < n;) {                               // Adler-32, deferred modulo
+            const size_t m = std::min<size_t>(5552, n - i);
+            for (size_t k = 0; k < m; ++k) { a += raw[pos + i + k]; b += a; }
+            a %= 65521u; b %= 65521u;
+            i += m;
+        }
+        pos += n;
+    }
+    put_be32(idat, (b << 16) | a);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<uint8_t> ihdr;
+    put_be32(ihdr, width); put_be32(ihdr, height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8-bit RGB, no interlace
+    const bool ok = std::fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr) && write_chunk(f, "IDAT", idat) &&
+                    write_chunk(f, "IEND", {});
+    return std::fclose(f) == 0 && ok;
+}
+bool write_png(const std::string& path, uint32_t width, uint32_t height, const float* rgba) {
+    std::vector<uint8_t> rgb(size_t(width) * height * 3);
+    quantize_rgb8(rgba, uint64_t(width) * height, rgb.data());
+    return write_png_rgb8(path, width, height, rgb.data());
+}
+
 }  // namespace raytrace
 
 // ============================================================================
@@ -504,6 +583,12 @@ int rtbh_box_contains_polygon(const float orig[3], float len2, const RtbTriangle
 }
 int rtbh_write_ppm(const char* path, uint32_t width, uint32_t height, const float* rgba) {
     return write_ppm(path, width, height, rgba) ? RTB_OK : RTB_ERR_INVALID;
+}
+int rtbh_write_png(const char* path, uint32_t width, uint32_t height, const float* rgba) {
+    return (path && rgba && write_png(path, width, height, rgba)) ? RTB_OK : RTB_ERR_INVALID;
+}
+int rtbh_write_png_rgb8(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb) {
+    return (path && rgb && write_png_rgb8(path, width, height, rgb)) ? RTB_OK : RTB_ERR_INVALID;
 }
 
 }  // extern "C"

@@ -91,5 +91,8 @@ bool box_contains_polygon(const Point& orig, float len2, const Triangle& t);
 // write_png's quantiser (raytrace.rs:1468-1473) with a PPM container.
 void quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb);
 bool write_ppm(const std::string& path, uint32_t width, uint32_t height, const float* rgba);
+// write_png (raytrace.rs:1460-1478): 8-bit RGB, no interlace; own encoder (stored deflate blocks).
+bool write_png_rgb8(const std::string& path, uint32_t width, uint32_t height, const uint8_t* rgb);
+bool write_png(const std::string& path, uint32_t width, uint32_t height, const float* rgba);
 
 }  // namespace raytrace

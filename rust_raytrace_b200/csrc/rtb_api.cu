@@ -100,7 +100,7 @@ void free_gpu_scene(GpuScene& g) {
     cudaSetDevice(g.device);
     if (g.stream) cudaStreamSynchronize(g.stream);
     cudaFree(g.d_nodes); cudaFree(g.d_nodes4); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
-    cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t);
+    cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t); cudaFree(g.d_rgb8);
     for (auto& l : g.lanes) {
         cudaFree(l.d_ws);
         if (l.done) cudaEventDestroy(l.done);
@@ -578,12 +578,16 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
     return RTB_OK;
 }
 
-int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* prim_out, float* t_out,
-               RtbStats* stats) {
+}  // extern "C"
+
+namespace {
+// rtb_render (f32 RGBA home) and rtb_render_rgb8 (quantised on the device, 3 bytes per pixel home) share one body.
+int render_host(rtb_scene* s, const RtbView* view, float* rgba_out, uint8_t* rgb8_out, uint32_t* prim_out, float* t_out,
+                RtbStats* stats) {
     if (!s) return fail(RTB_ERR_INVALID, "scene is NULL");
     int rc = check_view(view);
     if (rc != RTB_OK) return rc;
-    if (!rgba_out) return fail(RTB_ERR_INVALID, "rgba_out is NULL");
+    if (!rgba_out && !rgb8_out) return fail(RTB_ERR_INVALID, "output buffer is NULL");
     const double t0 = now_ms();
     const uint32_t world = (uint32_t)s->gpu.size();
     const uint32_t W = view->width, H = view->height;
@@ -613,6 +617,11 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
         const size_t pixels = (size_t)whole.my_tile_rows * RTB_TILE_H * W;
         rc = ensure_framebuffer(g, pixels, prim_out != nullptr, t_out != nullptr);
         if (rc != RTB_OK) return rc;
+        if (rgb8_out && g.rgb8_pixels < pixels) {
+            cudaFree(g.d_rgb8); g.d_rgb8 = nullptr; g.rgb8_pixels = 0;
+            RTB_CUDA(cudaMalloc(&g.d_rgb8, pixels * 3 + 16));
+            g.rgb8_pixels = pixels;
+        }
         if (!g.copy_stream) {
             RTB_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
             for (auto& e : g.chunk_ev) RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -625,6 +634,12 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
                            g.stream, pieces, n_lanes, &launches, &primary_total,
                            [&](uint32_t c, const ViewDev& vd, cudaStream_t ls) -> int {
             // the piece's bands go home on the copy stream as soon as its kernels are done
+            if (rgb8_out) {      // write_png's `(c * 255.) as u8` (raytrace.rs:1468-1473) on the piece's pixels, on its stream
+                const size_t first_px = (size_t)vd.band_begin * RTB_TILE_H * W, n_px = (size_t)vd.my_tile_rows * RTB_TILE_H * W;
+                int rcq = rtb_launch_quantize(g.d_rgba + first_px, n_px, g.d_rgb8 + 3 * first_px, ls);
+                if (rcq != RTB_OK) return rcq;
+                ++launches;
+            }
             RTB_CUDA(cudaEventRecord(g.chunk_ev[c], ls));
             RTB_CUDA(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c], 0));
             // local band b = image rows [(b*world + r)*8, +8); copy bands [band_begin, band_begin+n)
@@ -648,7 +663,8 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
                 return RTB_OK;
             };
             int rc2;
-            if ((rc2 = copy_plane(rgba_out, g.d_rgba, sizeof(float4))) != RTB_OK) return rc2;
+            if (rgba_out && (rc2 = copy_plane(rgba_out, g.d_rgba, sizeof(float4))) != RTB_OK) return rc2;
+            if (rgb8_out && (rc2 = copy_plane(rgb8_out, g.d_rgb8, 3)) != RTB_OK) return rc2;
             if (prim_out && (rc2 = copy_plane(prim_out, g.d_prim, sizeof(uint32_t))) != RTB_OK) return rc2;
             if (t_out && (rc2 = copy_plane(t_out, g.d_t, sizeof(float))) != RTB_OK) return rc2;
             return RTB_OK;
@@ -700,6 +716,19 @@ int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* pri
     st.n_gpus = world;
     if (stats) *stats = st;
     return RTB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rtb_render(rtb_scene* s, const RtbView* view, float* rgba_out, uint32_t* prim_out, float* t_out, RtbStats* stats) {
+    if (!rgba_out) return fail(RTB_ERR_INVALID, "rgba_out is NULL");
+    return render_host(s, view, rgba_out, nullptr, prim_out, t_out, stats);
+}
+
+int rtb_render_rgb8(rtb_scene* s, const RtbView* view, uint8_t* rgb_out, RtbStats* stats) {
+    if (!rgb_out) return fail(RTB_ERR_INVALID, "rgb_out is NULL");
+    return render_host(s, view, nullptr, rgb_out, nullptr, nullptr, stats);
 }
 
 int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, RtbStats* stats) {

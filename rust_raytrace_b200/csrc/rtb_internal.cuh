@@ -109,6 +109,8 @@ struct GpuScene {
     uint32_t* d_prim = nullptr;
     float* d_t = nullptr;
     size_t fb_pixels = 0;
+    uint8_t* d_rgb8 = nullptr;         // rtb_render_rgb8: quantised frame, 3 B per pixel
+    size_t rgb8_pixels = 0;
     uint32_t n_nodes = 0;
     uint32_t height = 0;
     float4* d_nodes4 = nullptr;

@@ -401,6 +401,21 @@ class B200RayCaster:
         ctx.finish()
         return ctx
 
+    def walk_rays_rgb8(self, v: RtbView, s: Scene, rgb, threads=1) -> ProgressCtx:
+        """walk_rays followed by write_png's quantiser, fused on the device (rtb_render_rgb8): `rgb` is H x W x 3 uint8."""
+        assert rgb.dtype == np.uint8 and rgb.size == v.width * v.height * 3 and rgb.flags["C_CONTIGUOUS"]
+        ctx = ProgressCtx(v.width, v.height, threads)
+        self._init(threads)
+        h = s.upload()
+        vv = RtbView.from_buffer_copy(v)
+        vv.seed = self.seed
+        st = RtbStats()
+        check(lib().rtb_render_rgb8(h, C.byref(vv), rgb.ctypes.data, C.byref(st)), "rtb_render_rgb8")
+        self.stats = st
+        ctx.update(0, v.height - 1, v.width * v.height, {"Rays": int(st.rays), "GPU ms": float(st.ms_render)})
+        ctx.finish()
+        return ctx
+
     def walk_rays_progressive(self, v: RtbView, s: Scene, data, threads=0) -> ProgressCtx:
         """Multi-sample frame with samples partitioned over the GPUs (rtb_render_progressive)."""
         ctx = ProgressCtx(v.width, v.height, threads)
@@ -414,6 +429,21 @@ class B200RayCaster:
         ctx.update(0, v.height - 1, v.width * v.height, {"Rays": int(st.rays), "GPU ms": float(st.ms_render)})
         ctx.finish()
         return ctx
+
+
+def write_png(path, img_size, data):
+    """write_png (raytrace.rs:1460-1478): 8-bit RGB PNG.  `data` is the f32 RGBA frame (quantised with the reference's
+    `(c*255.) as u8`) or an already quantised H x W x 3 uint8 frame (walk_rays_rgb8)."""
+    w, h = (img_size.width, img_size.height) if hasattr(img_size, "width") else img_size
+    data = np.asarray(data)
+    if data.dtype == np.uint8:
+        data = np.ascontiguousarray(data)
+        assert data.size == w * h * 3
+        check(lib().rtbh_write_png_rgb8(os.fsencode(path), w, h, data.ctypes.data), "rtbh_write_png_rgb8")
+    else:
+        data = np.ascontiguousarray(data, np.float32)
+        assert data.size == w * h * 4
+        check(lib().rtbh_write_png(os.fsencode(path), w, h, data.ctypes.data), "rtbh_write_png")
 
 
 def write_ppm(path, v_or_size, data):

@@ -410,3 +410,21 @@ def test_instanced_teapot_field_1m(R):
     assert np.array_equal(x[1], y[1]) and np.array_equal(bits(x[0]), bits(y[0]))
     s_host.release()
     s_inst.release()
+
+
+def test_render_rgb8_is_the_quantised_frame(R, O, scenes, tmp_path):
+    """rtb_render_rgb8 (render + write_png's quantiser fused on the device, 3 B/px home) against the oracle's frame
+    put through the oracle's quantiser; ragged height, and the PNG written from it decodes to the same pixels."""
+    from png_util import decode_png
+    s, _, obvh = scenes[False]
+    for (w, h) in ((640, 363), (1283, 721)):
+        v, ov = R.main_viewport(w, h, 5, 1), O.main_viewport(w, h, 5, 1)
+        rgb = np.zeros((h, w, 3), np.uint8)
+        caster = R.B200RayCaster(seed=5)
+        ctx = caster.walk_rays_rgb8(v, s, rgb)
+        rgba, _, _, st = obvh.render(ov, seed=5)
+        want = O.quantize_rgb8(rgba.reshape(-1, 4)).reshape(h, w, 3)
+        assert np.array_equal(rgb, want) and ctx.total_rays == st.rays
+    path = str(tmp_path / "frame.png")
+    R.write_png(path, (w, h), rgb)
+    assert np.array_equal(decode_png(path)[2], want)

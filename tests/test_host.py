@@ -154,3 +154,23 @@ def test_gpu_path_fails_loudly_without_a_device(R):
         with pytest.raises(RtbError) as e:
             call()
         assert e.value.code == -1
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (7, 5), (640, 360), (300, 73)])
+def test_write_png_holds_the_reference_quantisation(R, O, wh, tmp_path):
+    """write_png (raytrace.rs:1460-1478): the file must decode (zlib, CRC-checked) to exactly `(c*255.) as u8` of the
+    frame — the oracle's quantiser — for f32 input and for already quantised input; > 64 KiB frames span several
+    stored deflate blocks."""
+    w, h = wh
+    rs = np.random.RandomState(w * 1000 + h)
+    data = rs.uniform(-0.1, 1.1, (h, w, 4)).astype(np.float32)
+    data[0, 0, :3] = [np.nan, 1.0, 0.999999]
+    want = O.quantize_rgb8(data.reshape(-1, 4)).reshape(h, w, 3)
+    p1, p2 = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+    R.write_png(p1, (w, h), data)
+    R.write_png(p2, (w, h), want)
+    from png_util import decode_png
+    for p in (p1, p2):
+        gw, gh, px = decode_png(p)
+        assert (gw, gh) == (w, h) and np.array_equal(px, want)
+    assert open(p1, "rb").read() == open(p2, "rb").read()
