@@ -43,6 +43,10 @@ WORKLOADS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on (default)
     "teapot4k": ("teapot 4K multi-bounce (main.rs scene, 6721 tris, 3840x2160, maxdepth 5, 1 spp, shipped materials)",
                  3840, 2160, 5, 1, "bands"),
+    # configs[0]: the "circles" scene — not in the mounted reference; analytic spheres + shadow rays are
+    # this build's extension (rtb_ext.cu, one-kernel renderer), checked against the oracle's restatement of the same
+    "circles2k": ("circles 2K (extension): 64 analytic spheres + ground disk + one cube light, 2560x1440, maxdepth 2 "
+                  "(primary + 1 bounce) + one shadow ray per hit, 1 spp", 2560, 1440, 2, 1, "bands"),
     # configs[3]: ~1M triangles, GPU LBVH build + incoherent (mirror) bounces
     "field1m": ("teapot field, 156 instanced teapots = 985,921 tris, Reflective{0}, 2560x1440, maxdepth 5, 1 spp",
                 2560, 1440, 5, 1, "bands"),
@@ -117,6 +121,8 @@ class ClockSampler:
 # CPU reference arm (the oracle restatement running the reference's octree algorithm)
 # --------------------------------------------------------------------------------------------
 def build_scene(R, name):
+    if name == "circles2k":
+        return R.circles_scene()
     return R.teapot_field_scene() if name == "field1m" else R.main_scene(deterministic=False)
 
 
@@ -124,7 +130,12 @@ def oracle_scene(O, scene, name, cores):
     """Reference-algorithm mode (octree) wherever the reference's builder can handle the scene; the 1M-triangle
     scene cannot be built as an octree in reasonable time, there the oracle uses its own BVH."""
     accel = O.ACCEL_BVH if name == "field1m" else O.ACCEL_OCTREE
-    return O.Scene(scene.tris.view(O.TRI_DTYPE), accel, build_threads=cores), ("bvh" if accel == O.ACCEL_BVH else "octree")
+    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), accel, build_threads=cores)
+    if getattr(scene, "spheres", None) is not None:
+        osc.add_spheres(scene.spheres.view(O.SPH_DTYPE))
+    if getattr(scene, "light", None) is not None:
+        osc.set_light(*scene.light)
+    return osc, ("bvh" if accel == O.ACCEL_BVH else "octree")
 
 
 def cpu_reference(name, rows, threads=None, repeat=1):
@@ -151,6 +162,8 @@ def cpu_sample_rows(name):
         return (0, H)                 # the whole frame: 14.26 M rays, ~9 s on 16 host threads
     if name == "field1m":
         return (H // 2 + 100, H // 2 + 164)
+    if name == "circles2k":
+        return (0, H)                 # 64 spheres by brute force + a 160-triangle octree: a few seconds
     return (H // 2, H // 2 + 4)       # 64 spp: 4 rows x 7680 px x 64 samples
 
 
@@ -351,6 +364,32 @@ def run_gpu(args):
                "api": ("B200RayCaster.walk_rays_progressive -> rtb_render_progressive" if by_samples else
                        "B200RayCaster.walk_rays -> rtb_render") + " (pinned host image, scene resident)"}
         assert int(caster.stats.rays) == int(total_rays), (caster.stats.rays, total_rays)
+        if not by_samples:
+            # the same frame the way main.rs consumes it (walk_rays -> write_png): quantised on the device, 3 B/px home
+            host8 = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
+            rgb = host8.numpy()
+            for _ in range(3):
+                caster.walk_rays_rgb8(vv, sc_all, rgb, threads=args.gpus)
+            t0 = time.perf_counter()
+            rays8 = 0
+            for _ in range(e_steps):
+                rays8 += caster.walk_rays_rgb8(vv, sc_all, rgb, threads=args.gpus).total_rays
+            dt8 = time.perf_counter() - t0
+            e2e["rgb8"] = {"value": rays8 / dt8 / 1e6, "unit": "Mrays/s", "ms_per_frame": dt8 / e_steps * 1e3,
+                           "d2h_bytes_per_step": npix * 3,
+                           "api": "B200RayCaster.walk_rays_rgb8 -> rtb_render_rgb8 (write_png's quantiser fused on the device)"}
+        # scene assembly (the step in front of the path): finished host triangles vs mesh + instances assembled on the GPU
+        if name != "circles2k":
+            inf_host = sc_all.info()
+            sc_inst = R.teapot_field_scene(instanced=True) if name == "field1m" else R.main_scene(deterministic=False, instanced=True)
+            inf_inst = sc_inst.info()
+            e2e["scene_assembly"] = {
+                "host_triangle_array": {"ms_upload_and_cull": inf_host.ms_upload, "h2d_bytes": int(inf_host.n_tris) * 140},
+                "instanced_on_gpu": {"ms_assemble_and_cull": inf_inst.ms_upload,
+                                     "h2d_bytes": int(sc_inst.verts.nbytes + sc_inst.faces.nbytes + 80 * len(sc_inst.instances)
+                                                      + sc_inst.extra.nbytes + 140)},
+                "n_tris": int(inf_inst.n_tris), "n_refs": int(inf_inst.n_refs), "ms_build": inf_inst.ms_build}
+            sc_inst.release()
         sc_all.release()
     if world > 1:
         dist.barrier(group=host_group)
@@ -359,9 +398,13 @@ def run_gpu(args):
         hbm_peak, sm_max_mhz, peak_src = measured_peaks()
         # algorithmic bytes / FP32 lane-ops per ray = 32 B, 24 ops per AABB test; 80 B, 54 ops per exact
         # triangle test; 16 B per output pixel, 45 ops per generated ray.  Dominant kernel = k_wf_bounce (rank 0's launch).
-        b_rays = max(int(st2.bounce_rays), 1)
-        nb_node, nb_tri = st2.node_tests_bounce / b_rays, st2.tri_tests_bounce / b_rays
         n_node, n_tri = st2.node_tests / max(st2.rays, 1), st2.tri_tests / max(st2.rays, 1)
+        if name == "circles2k":      # one kernel per frame (rtb_ext.cu); its tests include the shadow rays'
+            dom_kernel, b_rays, nb_node, nb_tri = "k_trace_ext", max(int(st2.rays), 1), n_node, n_tri
+            stage_ms = np.array([0.0, 0.0, 0.0, ms_mine])
+        else:
+            dom_kernel, b_rays = "k_wf_bounce", max(int(st2.bounce_rays), 1)
+            nb_node, nb_tri = st2.node_tests_bounce / b_rays, st2.tri_tests_bounce / b_rays
         bounce_s = max(stage_ms[3], 1e-6) * 1e-3
         bytes_launch = b_rays * (nb_node * 32 + nb_tri * 80 + 16)
         ops_launch = b_rays * (nb_node * 24 + nb_tri * 54 + 45)
@@ -387,13 +430,14 @@ def run_gpu(args):
                                      if by_samples else f"8-row bands, band b -> rank b % {world}"),
                        "l2": "flushed between timed iterations (256 MiB fill); the scene is re-read from HBM each step",
                        "bvh": {"nodes": info.n_nodes, "leaves": info.n_leaves, "max_leaf": info.max_leaf,
-                               "height": info.tree_height, "ms_build": info.ms_build, "ms_upload": info.ms_upload},
+                               "height": info.tree_height, "prims": info.n_prims, "refs": info.n_refs,
+                               "ms_build": info.ms_build, "ms_upload": info.ms_upload},
                        "node_tests_per_ray": n_node, "tri_tests_per_ray": n_tri, "wall_s_timed_region": t_wall},
             "gpu_launches": args.steps * launches_per_step * world,
             "clocks": clocks,
             "e2e": e2e,
             "stages_ms": {k: float(v) for k, v in zip(_lib.RTB_STAGES, stage_ms)},
-            "roofline": {"bound": "hbm", "kernel": "k_wf_bounce", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "launch_ms": float(stage_ms[3]), "share_of_step": float(stage_ms[3] / max(stage_ms.sum(), 1e-9)),
                          "algorithmic_bytes_per_launch": bytes_launch,
@@ -401,7 +445,7 @@ def run_gpu(args):
                          "note": "algorithmic bytes = rays*(32*N_aabb + 80*N_tri + 16) are served by L1/L2 (the scene is "
                                  "cache resident; measured DRAM traffic is `traffic`), so `frac` can exceed 1 and the "
                                  "kernel's real bound is FP32/ALU issue under divergence: see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32_issue", "kernel": "k_wf_bounce", "achieved": ops_launch / bounce_s / 1e12,
+            "roofline_fp32": {"bound": "fp32_issue", "kernel": dom_kernel, "achieved": ops_launch / bounce_s / 1e12,
                               "peak": fp32_peak / 1e12, "unit": "Tlane-op/s", "frac": ops_launch / bounce_s / fp32_peak,
                               "whole_step_frac": step_ops / (ms_mine * 1e-3) / fp32_peak,
                               "lane_ops_per_ray": nb_node * 24 + nb_tri * 54 + 45},

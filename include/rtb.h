@@ -181,6 +181,27 @@ int rtb_assemble_triangles(const float* verts, uint32_t nverts, const uint32_t* 
 int rtb_cull_triangles(const RtbTriangle* tris, uint32_t n, const float root_orig[3], float root_len2,
                        uint32_t* keep_out, uint32_t* n_keep);
 
+/* ---- EXTENSION (BASELINE config 1 "circles scene, primary + shadow rays") -------------------
+ * Neither analytic spheres nor shadow rays exist in the mounted reference any more: the sphere primitive survives as
+ * the CollisionFace::{Side, Face} vestiges (raytrace.rs:311-318), the shadow test as the commented-out block of
+ * color_ray (raytrace.rs:1203-1224) with LightSource::get_shadow_ray (:594-610).  Their semantics are therefore
+ * defined by this build (rust_raytrace_b200/csrc/rtb_ext.cu, restated in the oracle) and checked oracle-vs-GPU only.
+ * Scenes that use them are rendered by the one-kernel extension renderer, through the same rtb_render* entry points. */
+typedef struct RtbSphere {
+    float center[3];
+    float radius;             /* > 0 */
+    uint32_t kind;            /* RTB_SOLID / RTB_MATTE / RTB_REFLECTIVE */
+    float color[3];
+    float alpha;
+    float scattering;
+} RtbSphere;
+/* rtb_scene_create plus n_spheres analytic spheres; primitive ids: triangles 1..n-1, sphere j = n + j. */
+int rtb_scene_create_ext(const RtbTriangle* tris, uint32_t n, const RtbSphere* spheres, uint32_t n_spheres,
+                         const float root_orig[3], float root_len2, rtb_scene** out);
+/* Scene.lights = Some(LightSource{orig, len2}) (raytrace.rs:594-597): every hit casts one shadow ray towards a random
+ * point of the cube [orig, orig+len2)^3 and is black where any other object intersects that ray.  orig NULL = none. */
+int rtb_scene_set_light(rtb_scene* s, const float orig[3], float len2);
+
 int rtb_scene_info(const rtb_scene* s, RtbSceneInfo* out);
 void rtb_scene_destroy(rtb_scene* s);
 /* Debug/inspection: copy the BVH of GPU 0 back (nodes: n_nodes*8 floats; prim_order: n_refs u32

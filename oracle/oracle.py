@@ -35,6 +35,10 @@ TRI_DTYPE = np.dtype(
     ]
 )
 assert TRI_DTYPE.itemsize == 140
+# EXTENSION: analytic sphere, mirror of OrSphere / RtbSphere (40 bytes)
+SPH_DTYPE = np.dtype([("center", "<f4", (3,)), ("radius", "<f4"), ("kind", "<u4"), ("color", "<f4", (3,)),
+                      ("alpha", "<f4"), ("scattering", "<f4")])
+assert SPH_DTYPE.itemsize == 40
 
 
 class OrView(C.Structure):
@@ -120,6 +124,10 @@ def lib():
     L.or_scene_create.argtypes = [vp, C.c_uint32, C.c_int, f3, C.c_float, C.c_uint32, C.c_uint32, C.c_int]
     L.or_scene_create.restype = vp
     L.or_scene_destroy.argtypes = [vp]
+    L.or_scene_add_spheres.argtypes = [vp, vp, C.c_uint32]
+    L.or_scene_add_spheres.restype = None
+    L.or_scene_set_light.argtypes = [vp, f3, C.c_float]
+    L.or_scene_set_light.restype = None
     L.or_scene_tree_stats.argtypes = [vp, C.POINTER(OrTreeStats)]
     L.or_scene_closest_hit.argtypes = [vp, f3, f3, C.POINTER(C.c_float)]
     L.or_scene_closest_hit.restype = C.c_uint32
@@ -250,6 +258,17 @@ class Scene:
         if getattr(self, "h", None):
             lib().or_scene_destroy(self.h)
             self.h = None
+
+    def add_spheres(self, spheres):
+        """EXTENSION: analytic spheres, primitive ids len(tris) + j."""
+        spheres = np.ascontiguousarray(spheres, SPH_DTYPE)
+        lib().or_scene_add_spheres(self.h, spheres.ctypes.data, len(spheres))
+        return self
+
+    def set_light(self, orig, len2):
+        """EXTENSION: Scene.lights = Some(LightSource{orig, len2}) (raytrace.rs:594-610, :1203-1224); None removes it."""
+        lib().or_scene_set_light(self.h, None if orig is None else _f3(orig), float(len2))
+        return self
 
     def tree_stats(self) -> OrTreeStats:
         st = OrTreeStats()

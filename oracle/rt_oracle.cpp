@@ -244,6 +244,31 @@ static inline V3 tri_normal(const Tri& tr, int face) {                          
 }
 
 /* ------------------------------------------------------------------ */
+/* EXTENSION: analytic sphere.  The mounted      */
+/* reference has no sphere primitive any more (only the      */
+/* vestiges CollisionFace::{Side,Face}, rs:311-318, and circles_2k.png  */
+/* of an older revision), so this definition is the build's own; it     */
+/* follows Triangle::intersects' conventions (t < 0 rejects, literal    */
+/* comparisons, normal flipped for the back face).                      */
+/* ------------------------------------------------------------------ */
+struct Sph { V3 c; float r; uint32_t kind; V3 color; float alpha, scattering; };
+
+static inline V3 sph_normal_out(const Sph& s, V3 p) { return vunit(vsub(p, s.c)); }
+static inline int sph_intersects(const Sph& s, const Ray& r, float* t_out, V3* p_out) {
+    V3 oc = vsub(r.orig, s.c);
+    float b = vdot(oc, r.dir);                       /* |dir| = 1: t^2 + 2bt + c = 0 */
+    float c = vlen2(oc) - s.r * s.r;
+    float disc = b * b - c;
+    if (disc < 0.0f) return F_NONE;
+    float sq = sqrtf(disc);
+    float t = (-b) - sq;                             /* near root, else the far one (origin inside) */
+    if (t < 0.0f) { t = (-b) + sq; if (t < 0.0f) return F_NONE; }
+    V3 p = ray_at(r, t);
+    *t_out = t; *p_out = p;
+    return (vdot(r.dir, sph_normal_out(s, p)) > 0.0f) ? F_BACK : F_FRONT;
+}
+
+/* ------------------------------------------------------------------ */
 /* scene generators — rs:464-592                                        */
 /* ------------------------------------------------------------------ */
 static const float PI_F = 3.14159265358979323846f;
@@ -634,6 +659,33 @@ struct OBvh {
         nodes.clear();
         if (!order.empty()) build(tris, 0, (uint32_t)order.size(), 1e-3 * std::max(1.0, m / 16.0));
     }
+    /* does any triangle other than `exclude` intersect the ray (any t >= 0)?  (shadow rays) */
+    bool any_hit(const std::vector<Tri>& tris, const Ray& r, uint32_t exclude) const {
+        if (nodes.empty()) return false;
+        int32_t stack[128]; int sp = 0; stack[sp++] = 0;
+        double o[3] = {r.orig.x, r.orig.y, r.orig.z}, d[3] = {r.dir.x, r.dir.y, r.dir.z};
+        while (sp) {
+            const BNode& n = nodes[stack[--sp]];
+            double t0 = 0.0, t1 = 1e300;
+            bool miss = false;
+            for (int k = 0; k < 3 && !miss; k++) {
+                if (d[k] == 0.0) { if (o[k] < n.lo[k] || o[k] > n.hi[k]) miss = true; continue; }
+                double a = (n.lo[k] - o[k]) / d[k], b = (n.hi[k] - o[k]) / d[k];
+                if (a > b) std::swap(a, b);
+                t0 = std::max(t0, a - 1e-6); t1 = std::min(t1, b + 1e-6);
+                if (t0 > t1) miss = true;
+            }
+            if (miss) continue;
+            if (n.left < 0) {
+                for (uint32_t i = n.first; i < n.first + n.count; i++) {
+                    uint32_t tnum = order[i];
+                    float t; V3 p;
+                    if (tnum != exclude && tri_intersects(tris[tnum], r, &t, &p) != F_NONE) return true;
+                }
+            } else if (sp + 2 <= 128) { stack[sp++] = n.left; stack[sp++] = n.right; }
+        }
+        return false;
+    }
     Hit intersect(const std::vector<Tri>& tris, const Ray& r, Counters& c) const {
         Hit acc; acc.some = false; acc.t = 0; acc.p = mk(0, 0, 0); acc.face = 0; acc.idx = 0;
         if (nodes.empty()) return acc;
@@ -680,6 +732,10 @@ struct OBvh {
 /* ------------------------------------------------------------------ */
 struct OrScene {
     std::vector<Tri> tris;
+    std::vector<Sph> spheres;     /* EXTENSION: primitive ids tris.size() + j */
+    bool has_light = false;       /* Scene.lights: Option<LightSource> (rs:594-597, use commented out at rs:1204-1224) */
+    V3 light_orig = {0, 0, 0};
+    float light_len2 = 0;
     int accel;
     BBox* root;       /* OCTREE / TRIVIAL */
     OBvh bvh;         /* BVH */
@@ -692,8 +748,35 @@ static inline Hit scene_hit(const OrScene& s, const Ray& r, Counters& c) {
     Hit h;
     if (s.accel == OR_ACCEL_BVH) h = s.bvh.intersect(s.tris, r, c);
     else h = bb_intersect(*s.root, s.tris, r, c);
+    /* EXTENSION: analytic spheres, ids after the triangles; strict < keeps the lowest id on exact-t ties */
+    for (uint32_t j = 0; j < s.spheres.size(); j++) {
+        float t; V3 p;
+        int face = sph_intersects(s.spheres[j], r, &t, &p);
+        if (face != F_NONE && (!h.some || t < h.t)) {
+            h.some = true; h.t = t; h.p = p; h.face = face; h.idx = (uint32_t)s.tris.size() + j;
+        }
+    }
     if (h.some && !(h.t < std::numeric_limits<float>::infinity())) c.nan_t++;
     return h;
+}
+
+/* The shadow test of the commented-out block rs:1204-1224: does ANY object other than the one that was hit
+ * intersect the light ray (anywhere along it: `intersects(..).is_some()`, no distance limit)?  The old code
+ * collected candidates with get_all_objects_for_ray, whose BTreeMap drops leaves with equal tmin;
+ * the oracle tests every object, which is what that code means to do. */
+static bool scene_any_hit(const OrScene& s, const Ray& r, uint32_t exclude) {
+    if (s.accel == OR_ACCEL_BVH) { if (s.bvh.any_hit(s.tris, r, exclude)) return true; }
+    else {
+        for (uint32_t i = 1; i < s.tris.size(); i++) {
+            float t; V3 p;
+            if (i != exclude && tri_intersects(s.tris[i], r, &t, &p) != F_NONE) return true;
+        }
+    }
+    for (uint32_t j = 0; j < s.spheres.size(); j++) {
+        float t; V3 p;
+        if ((uint32_t)s.tris.size() + j != exclude && sph_intersects(s.spheres[j], r, &t, &p) != F_NONE) return true;
+    }
+    return false;
 }
 
 static V3 project_ray(const Ray& r, const OrScene& s, uint32_t depth, Rng& g, Counters& c,
@@ -701,20 +784,44 @@ static V3 project_ray(const Ray& r, const OrScene& s, uint32_t depth, Rng& g, Co
 
 static V3 color_ray(const Ray& r, const OrScene& s, uint32_t objidx, V3 point, int face, uint32_t depth,
                     Rng& g, Counters& c) {                                                     /* rs:1199-1254 */
-    const Tri& tr = s.tris[objidx];
-    if (face == F_EDGEFRONT || face == F_EDGEBACK) return make_color(0, 0, 0);                /* rs:450-459 */
-    switch (tr.kind) {
+    const bool is_sph = objidx >= s.tris.size();
+    uint32_t kind; V3 color; float alpha, scattering; V3 normal;
+    if (is_sph) {
+        const Sph& sp = s.spheres[objidx - s.tris.size()];
+        kind = sp.kind; color = sp.color; alpha = sp.alpha; scattering = sp.scattering;
+        normal = sph_normal_out(sp, point);
+        if (face == F_BACK) normal = vmul(normal, -1.0f);
+    } else {
+        const Tri& tr = s.tris[objidx];
+        kind = tr.kind; color = tr.color; alpha = tr.alpha; scattering = tr.scattering;
+        normal = tri_normal(tr, face);
+    }
+    /* `shadowed` is evaluated first, for every hit (rs:1203-1224, LightSource::get_shadow_ray rs:600-610): a point of
+     * the light cube [orig, orig + len2)^3, the ray starts 0.005..0.01 off the surface along the facing normal */
+    bool shadowed = false;
+    if (s.has_light) {
+        float rx = g.next_f32(), ry = g.next_f32(), rz = g.next_f32();
+        V3 adj = mk(s.light_orig.x + rx * s.light_len2, s.light_orig.y + ry * s.light_len2, s.light_orig.z + rz * s.light_len2);
+        V3 dir = vunit(vsub(adj, point));
+        V3 smudge = vmul(normal, 0.005f * (g.next_f32() + 1.0f));
+        Ray light_ray = make_ray(vadd(point, smudge), dir);
+        shadowed = scene_any_hit(s, light_ray, objidx);
+    }
+    V3 black = make_color(0, 0, 0);
+    if (face == F_EDGEFRONT || face == F_EDGEBACK) return black;                               /* rs:450-459 */
+    V3 base = shadowed ? black : color;
+    switch (kind) {
     case OR_SOLID:
-        return tr.color;
+        return base;
     case OR_MATTE: {
-        Ray nr = lambertian_ray(point, tri_normal(tr, face), g);
+        Ray nr = lambertian_ray(point, normal, g);
         V3 sub = project_ray(nr, s, depth - 1, g, c, nullptr, nullptr);
-        return mix_color(tr.color, sub, tr.alpha);
+        return mix_color(base, sub, alpha);
     }
     default: {
-        Ray nr = reflect_ray(point, tri_normal(tr, face), r.dir, tr.scattering, g);
+        Ray nr = reflect_ray(point, normal, r.dir, scattering, g);
         V3 sub = project_ray(nr, s, depth - 1, g, c, nullptr, nullptr);
-        return mix_color(tr.color, sub, tr.alpha);
+        return mix_color(base, sub, alpha);
     }
     }
 }
@@ -965,6 +1072,22 @@ OrScene* or_scene_create(const OrTriangle* tris, uint32_t n, int accel, const fl
 }
 
 void or_scene_destroy(OrScene* s) { delete s; }
+
+/* EXTENSION: analytic spheres (primitive ids n_tris + j) and the light of the reference's
+ * commented-out shadow code. */
+void or_scene_add_spheres(OrScene* s, const OrSphere* sp, uint32_t n) {
+    for (uint32_t j = 0; j < n; j++) {
+        Sph q;
+        q.c = mk(sp[j].center[0], sp[j].center[1], sp[j].center[2]); q.r = sp[j].radius;
+        q.kind = sp[j].kind; q.color = mk(sp[j].color[0], sp[j].color[1], sp[j].color[2]);
+        q.alpha = sp[j].alpha; q.scattering = sp[j].scattering;
+        s->spheres.push_back(q);
+    }
+}
+void or_scene_set_light(OrScene* s, const float orig[3], float len2) {
+    s->has_light = orig != nullptr;
+    if (orig) { s->light_orig = mk(orig[0], orig[1], orig[2]); s->light_len2 = len2; }
+}
 
 void or_scene_tree_stats(const OrScene* s, OrTreeStats* out) {
     memset(out, 0, sizeof *out);

@@ -120,6 +120,12 @@ OrScene* or_scene_create(const OrTriangle* tris, uint32_t n, int accel,
                          const float root_orig[3], float root_len2,
                          uint32_t maxdepth, uint32_t minobjs, int build_threads);
 void or_scene_destroy(OrScene* s);
+/* EXTENSION (not in the mounted reference, see rt_oracle.cpp): analytic spheres, primitive ids
+ * n_tris + j, and the light source of the reference's commented-out shadow code (raytrace.rs:594-610, :1203-1224);
+ * orig == NULL removes the light. */
+typedef struct OrSphere { float center[3]; float radius; uint32_t kind; float color[3]; float alpha; float scattering; } OrSphere;
+void or_scene_add_spheres(OrScene* s, const OrSphere* spheres, uint32_t n);
+void or_scene_set_light(OrScene* s, const float orig[3], float len2);
 void or_scene_tree_stats(const OrScene* s, OrTreeStats* out);
 /* Closest hit for one explicit ray (dir is normalised by make_ray); returns prim id, 0 = miss. */
 uint32_t or_scene_closest_hit(const OrScene* s, const float orig[3], const float dir[3], float* t_out);

@@ -96,6 +96,11 @@ class RtbSurface(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("color", C.c_float * 3), ("alpha", C.c_float), ("scattering", C.c_float)]
 
 
+# EXTENSION (include/rtb.h): analytic sphere, 40 bytes
+SPH_DTYPE = np.dtype([("center", "<f4", (3,)), ("radius", "<f4"), ("kind", "<u4"), ("color", "<f4", (3,)),
+                      ("alpha", "<f4"), ("scattering", "<f4")])
+
+
 class RtbMeshInstance(C.Structure):
     _fields_ = [("transform_rows", C.c_float * 9), ("offset", C.c_float * 3), ("scale", C.c_float),
                 ("edge_thickness", C.c_float), ("kind", C.c_uint32), ("color", C.c_float * 3), ("alpha", C.c_float),
@@ -106,7 +111,7 @@ class RtbMeshInstance(C.Structure):
 RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render_rgb8", "rtb_scene_create_instanced", "rtb_assemble_triangles",
-    "rtb_cull_triangles", "rtb_render", "rtb_render_device", "rtb_render_progressive",
+    "rtb_cull_triangles", "rtb_scene_create_ext", "rtb_scene_set_light", "rtb_render", "rtb_render_device", "rtb_render_progressive",
     "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
 ]
 RTBH_SYMBOLS = [
@@ -146,6 +151,8 @@ def lib():
     L.rtb_scene_create_instanced.argtypes = [vp, u32, vp, u32, vp, u32, vp, u32, f, C.c_float, C.POINTER(vp)]
     L.rtb_assemble_triangles.argtypes = [vp, u32, vp, u32, vp, u32, vp]
     L.rtb_cull_triangles.argtypes = [vp, u32, f, C.c_float, vp, C.POINTER(u32)]
+    L.rtb_scene_create_ext.argtypes = [vp, u32, vp, u32, f, C.c_float, C.POINTER(vp)]
+    L.rtb_scene_set_light.argtypes = [vp, f, C.c_float]
     L.rtb_scene_info.argtypes = [vp, C.POINTER(RtbSceneInfo)]
     L.rtb_scene_destroy.argtypes = [vp]
     L.rtb_scene_destroy.restype = None

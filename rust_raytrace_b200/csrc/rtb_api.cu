@@ -181,6 +181,8 @@ uint64_t owned_pixels(const ViewDev& vd) {
 // counters->rays afterwards (the wavefront counts bounce rays on the device, primaries on the host).
 int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd, float4* d_rgba, uint32_t* d_prim,
                  float* d_t, cudaStream_t st, uint32_t* launches, uint64_t* primary_rays) {
+    if (g.has_spheres || g.ext.has_light)      // EXTENSION scenes: analytic spheres / shadow rays (rtb_ext.cu)
+        return rtb_launch_trace_ext(scene_dev(g, n_prims), vd, g.ext, d_rgba, d_prim, d_t, g.d_counters, st, launches);
     if (vd.flags & RTB_FLAG_MEGAKERNEL)
         return rtb_launch_trace(scene_dev(g, n_prims), vd, d_rgba, d_prim, d_t, g.d_counters, st, launches);
     const uint32_t n_slots = vd.my_tile_rows * 2u * ((vd.width + 7u) / 8u) * 32u;
@@ -325,7 +327,9 @@ struct TriSource {
     const RtbMeshInstance* inst = nullptr; uint32_t n_inst = 0;
     const RtbTriangle* extra = nullptr; uint32_t n_extra = 0;
     bool instanced = false;
-    uint32_t total() const { return instanced ? 1u + nfaces * n_inst + n_extra : n; }
+    const RtbSphere* spheres = nullptr; uint32_t n_spheres = 0;   // EXTENSION: appended as pseudo-triangles
+    uint32_t n_triangles() const { return instanced ? 1u + nfaces * n_inst + n_extra : n; }
+    uint32_t total() const { return n_triangles() + n_spheres; }
 };
 
 cudaError_t upload(void** d, const void* h, size_t bytes, cudaStream_t st) {
@@ -334,8 +338,38 @@ cudaError_t upload(void** d, const void* h, size_t bytes, cudaStream_t st) {
     return e;
 }
 
+// EXTENSION: a sphere as the pseudo-`Triangle` the builder and the extension renderer understand (rtb_ext.cu):
+// norm = 0 marks it, incenter = centre, bounding_r2 = r*r, corners span its AABB, kind carries RTB_PRIM_SPHERE.
+RtbTriangle sphere_record(const RtbSphere& sp) {
+    RtbTriangle t;
+    std::memset(&t, 0, sizeof t);
+    for (int k = 0; k < 3; ++k) {
+        t.incenter[k] = sp.center[k];
+        t.corners[k] = sp.center[k] - sp.radius; t.corners[3 + k] = sp.center[k] + sp.radius; t.corners[6 + k] = t.corners[k];
+        t.color[k] = sp.color[k];
+    }
+    t.bounding_r2 = sp.radius * sp.radius;
+    t.edge_thickness = -1.0f;
+    t.kind = (sp.kind & 0xffu) | RTB_PRIM_SPHERE;
+    t.alpha = sp.alpha;
+    t.scattering = sp.scattering;
+    return t;
+}
+
+int produce_base_triangles(const TriSource& src, RtbTriangle* d_tris, cudaStream_t st);
+
 // Fills d_tris[0 .. src.total()) on the current device.
 int produce_triangles(const TriSource& src, RtbTriangle* d_tris, cudaStream_t st) {
+    int rc = produce_base_triangles(src, d_tris, st);
+    if (rc != RTB_OK || src.n_spheres == 0) return rc;
+    std::vector<RtbTriangle> rec(src.n_spheres);
+    for (uint32_t j = 0; j < src.n_spheres; ++j) rec[j] = sphere_record(src.spheres[j]);
+    RTB_CUDA(cudaMemcpyAsync(d_tris + src.n_triangles(), rec.data(), sizeof(RtbTriangle) * rec.size(), cudaMemcpyHostToDevice, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    return RTB_OK;
+}
+
+int produce_base_triangles(const TriSource& src, RtbTriangle* d_tris, cudaStream_t st) {
     if (!src.instanced) {
         if (src.n) RTB_CUDA(cudaMemcpyAsync(d_tris, src.tris, sizeof(RtbTriangle) * src.n, cudaMemcpyHostToDevice, st));
         RTB_CUDA(cudaStreamSynchronize(st));
@@ -415,6 +449,7 @@ int scene_create_common(const TriSource& src, const float root_orig[3], float ro
         g.n_nodes = br.n_nodes;
         g.height = br.tree_height;
         g.d_nodes4 = br.d_nodes4; g.n_nodes4 = br.n_nodes4; g.depth4 = br.depth4;
+        g.has_spheres = src.n_spheres > 0;
         if (rc != RTB_OK) return bail(rc);
         if (gi == 0) {
             s->info.n_nodes = br.n_nodes; s->info.n_leaves = br.n_leaves; s->info.max_leaf = br.max_leaf;
@@ -450,6 +485,29 @@ int check_mesh_args(const float* verts, uint32_t nverts, const uint32_t* faces, 
     return RTB_OK;
 }
 }  // namespace
+
+int rtb_scene_create_ext(const RtbTriangle* tris, uint32_t n, const RtbSphere* spheres, uint32_t n_spheres,
+                         const float root_orig[3], float root_len2, rtb_scene** out) {
+    if (!out) return fail(RTB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if ((n > 0 && !tris) || (n_spheres > 0 && !spheres)) return fail(RTB_ERR_INVALID, "NULL primitive array");
+    if (n == 0 && n_spheres > 0) return fail(RTB_ERR_INVALID, "primitive 0 must be the dummy triangle (ids: triangles 1..n-1, spheres n..)");
+    for (uint32_t j = 0; j < n_spheres; ++j)
+        if (!(spheres[j].radius > 0.0f) || (spheres[j].kind & ~0xffu)) return fail(RTB_ERR_INVALID, "bad sphere " + std::to_string(j));
+    TriSource src;
+    src.tris = tris; src.n = n; src.spheres = spheres; src.n_spheres = n_spheres;
+    return scene_create_common(src, root_orig, root_len2, out);
+}
+
+int rtb_scene_set_light(rtb_scene* s, const float orig[3], float len2) {
+    if (!s) return fail(RTB_ERR_INVALID, "scene is NULL");
+    for (auto& g : s->gpu) {
+        g.ext.has_light = orig ? 1u : 0u;
+        for (int k = 0; k < 3; ++k) g.ext.light[k] = orig ? orig[k] : 0.0f;
+        g.ext.light[3] = orig ? len2 : 0.0f;
+    }
+    return RTB_OK;
+}
 
 int rtb_scene_create_instanced(const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces,
                                const RtbMeshInstance* inst, uint32_t n_inst, const RtbTriangle* extra,

@@ -74,6 +74,14 @@ struct ViewDev {
     uint32_t compact;        // 1: output rows are packed (own bands only), 0: full-frame indexing
 };
 
+// EXTENSION (rtb_ext.cu): analytic spheres travel as pseudo-triangles tagged in `kind`; the light of the reference's
+// commented-out shadow code (raytrace.rs:594-610).
+#define RTB_PRIM_SPHERE 0x100u
+struct ExtParams {
+    float light[4];        // LightSource: orig xyz, len2
+    uint32_t has_light;
+};
+
 struct TraceCounters {
     unsigned long long rays;
     unsigned long long node_tests;
@@ -117,6 +125,9 @@ struct GpuScene {
     uint32_t n_nodes4 = 0, depth4 = 0;
     GpuLane lanes[RTB_MAX_LANES];
     cudaEvent_t fork_ev = nullptr;
+    // scenes with analytic spheres or a light are rendered by the extension renderer (rtb_ext.cu)
+    bool has_spheres = false;
+    ExtParams ext = {};
 };
 
 struct rtb_scene {
@@ -167,6 +178,9 @@ int rtb_launch_cull(const RtbTriangle* d_tris, uint32_t n, const float root_orig
 // Launches the trace kernel for the tile rows owned by (tile_rank, tile_world).
 int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint32_t* d_prim, float* d_t,
                      TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches);
+// ---- implemented in rtb_ext.cu --------------------------------------------------
+int rtb_launch_trace_ext(const SceneDev& sc, const ViewDev& vw, const ExtParams& ex, float4* d_rgba, uint32_t* d_prim,
+                         float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches);
 // ---- implemented in rtb_wavefront.cu -------------------------------------------
 // The default renderer: raygen / persistent trace / shade+compact stages per bounce level.
 // counters->rays receives the BOUNCE rays only; the caller adds the primary rays (valid pixels x samples).

@@ -140,7 +140,7 @@ __global__ void k_split_refs(const RtbTriangle* __restrict__ tris, const uint32_
     const float4 l = plo[i], h = phi[i];
     uint32_t out = EMIT ? offset[i] : 0u;
     uint32_t made = 0;
-    if (fmaxf(fmaxf(h.x - l.x, h.y - l.y), h.z - l.z) <= max_len) {
+    if (fmaxf(fmaxf(h.x - l.x, h.y - l.y), h.z - l.z) <= max_len || (tris[keep[i]].kind & RTB_PRIM_SPHERE)) {   // a sphere's corners are its AABB, not a triangle
         if (EMIT) { rlo[out] = l; rhi[out] = h; rkeep[out] = keep[i]; }
         made = 1;
     } else {
@@ -717,9 +717,12 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
 static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n, cudaStream_t stream,
                       bool force_karras, BuildResult* out) {
     *out = BuildResult();
-    cudaEvent_t e0, e1;
+    // device time of the build = the bounds/split phase (s0..s1) + everything after the allocations (e0..e1)
+    cudaEvent_t e0, e1, s0, s1;
     RTB_CUDA(cudaEventCreate(&e0));
     RTB_CUDA(cudaEventCreate(&e1));
+    RTB_CUDA(cudaEventCreate(&s0));
+    RTB_CUDA(cudaEventCreate(&s1));
     const uint32_t B = 256;
     uint32_t launches = 0;
 
@@ -744,16 +747,18 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     DevBuf<uint32_t> ref_keep;
     RTB_CUDA(scratch.alloc(1));
     RTB_CUDA(plo.alloc(n)); RTB_CUDA(phi.alloc(n));
-    RTB_CUDA(cudaEventRecord(e0, stream));
+    DevBuf<uint32_t> cnt, off;
+    DevBuf<uint8_t> scan_tmp;
+    if (n > 0 && benv.split_div > 0) {
+        RTB_CUDA(cnt.alloc(n + 1)); RTB_CUDA(off.alloc(n + 1));
+        RTB_CUDA(scan_tmp.alloc(rtbsort::scan_tmp_bytes<uint32_t>(n + 1)));
+    }
+    RTB_CUDA(cudaEventRecord(s0, stream));
     k_init_scratch<<<1, 32, 0, stream>>>(scratch.p); ++launches;
     out->n_refs = n;
     if (n > 0) {
         k_prim_bounds<<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, n, plo.p, phi.p, scratch.p); ++launches;
         if (benv.split_div > 0) {
-            DevBuf<uint32_t> cnt, off;
-            DevBuf<uint8_t> scan_tmp;
-            RTB_CUDA(cnt.alloc(n + 1)); RTB_CUDA(off.alloc(n + 1));
-            RTB_CUDA(scan_tmp.alloc(rtbsort::scan_tmp_bytes<uint32_t>(n + 1)));
             const float inv_div = 1.0f / (float)benv.split_div;
             k_split_refs<false><<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, n, plo.p, phi.p, scratch.p, inv_div, cnt.p,
                                                               nullptr, nullptr, nullptr, nullptr); ++launches;
@@ -767,7 +772,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
                 RTB_CUDA(rlo.alloc(n_refs)); RTB_CUDA(rhi.alloc(n_refs)); RTB_CUDA(ref_keep.alloc(n_refs));
                 k_split_refs<true><<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, n, plo.p, phi.p, scratch.p, inv_div, nullptr,
                                                                  off.p, rlo.p, rhi.p, ref_keep.p); ++launches;
-                RTB_CUDA(cudaStreamSynchronize(stream));      // cnt/off/old boxes are freed at the end of this scope
+                RTB_CUDA(cudaStreamSynchronize(stream));      // the old boxes are freed at the end of this scope
                 std::swap(plo.p, rlo.p); std::swap(phi.p, rhi.p);
                 d_keep = ref_keep.p;
                 n = n_refs;
@@ -775,6 +780,8 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
             }
         }
     }
+
+    RTB_CUDA(cudaEventRecord(s1, stream));
 
     // final arrays (owned by the scene afterwards)
     const uint32_t n_alloc = n ? n : 1;
@@ -798,7 +805,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaMemcpyAsync(out->d_nodes4, h4, sizeof h4, cudaMemcpyHostToDevice, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
         out->n_nodes4 = 1;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1);
         return RTB_OK;
     }
 
@@ -836,6 +843,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
                                                                           rtbsort::scan_tmp_bytes<unsigned long long>(n)));
     RTB_CUDA(sort_tmp.alloc(tmp_bytes));
 
+    RTB_CUDA(cudaEventRecord(e0, stream));
     k_morton<<<cdiv(n, B), B, 0, stream>>>(plo.p, phi.p, n, scratch.p, keys.p, vals.p); ++launches;
     {
         bool in_b = false;
@@ -924,8 +932,11 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     RTB_CUDA(cudaMemcpyAsync(&h, scratch.p, sizeof h, cudaMemcpyDeviceToHost, stream));
     RTB_CUDA(cudaStreamSynchronize(stream));
     RTB_CUDA(cudaGetLastError());
+    float ms_split = 0.f;
     RTB_CUDA(cudaEventElapsedTime(&out->ms_build, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    RTB_CUDA(cudaEventElapsedTime(&ms_split, s0, s1));
+    out->ms_build += ms_split;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1);
 
     auto dec = [](uint32_t o) { uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; float f; memcpy(&f, &u, 4); return f; };
     for (int k = 0; k < 3; ++k) { out->lo[k] = dec(h.scene_lo[k]); out->hi[k] = dec(h.scene_hi[k]); }

@@ -190,7 +190,7 @@ __global__ void k_cull_flags(const RtbTriangle* __restrict__ tris, uint32_t n, f
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     uint32_t keep = 0u;
-    if (i >= 1u && i < n) keep = (root_len2 > 0.f) ? (box_contains_polygon_dev(mk(root.x, root.y, root.z), root_len2, tris[i]) ? 1u : 0u) : 1u;
+    if (i >= 1u && i < n) keep = (root_len2 > 0.f && !(tris[i].kind & RTB_PRIM_SPHERE)) ? (box_contains_polygon_dev(mk(root.x, root.y, root.z), root_len2, tris[i]) ? 1u : 0u) : 1u;
     flags[i] = keep;    // flags[n] = 0 closes the exclusive scan
 }
 __global__ void k_compact_keep(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t n,

@@ -23,7 +23,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (RTB_FLAG_STATS, RTB_FLAG_SUM_ONLY, RTB_MATTE, RTB_REFLECTIVE, RTB_SOLID, TRI_DTYPE, RtbMeshInstance,
+from ._lib import (RTB_FLAG_STATS, RTB_FLAG_SUM_ONLY, RTB_MATTE, RTB_REFLECTIVE, RTB_SOLID, SPH_DTYPE, TRI_DTYPE, RtbMeshInstance,
                    RtbSceneInfo, RtbStats, RtbSurface, RtbView, check, lib)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
@@ -198,10 +198,13 @@ class Scene:
     """`Scene{tris, boxes, ..}`.  `boxes` keeps only what the GPU path needs of the octree:
     the root cube (orig, len2) used for the reference's visibility cull; None disables it."""
 
-    def __init__(self, tris, boxes=((0.0, 0.0, 20.1), 20.0)):
+    def __init__(self, tris, boxes=((0.0, 0.0, 20.1), 20.0), spheres=None, light=None):
         self.tris = np.ascontiguousarray(tris, TRI_DTYPE)
         self.boxes = boxes
         self._h = None
+        # EXTENSION (include/rtb.h): analytic spheres (ids len(tris) + j) and `lights: Option<LightSource>` = (orig, len2)
+        self.spheres = None if spheres is None else np.ascontiguousarray(spheres, SPH_DTYPE)
+        self.light = light
 
     # device residency -----------------------------------------------------
     def upload(self):
@@ -211,9 +214,21 @@ class Scene:
                 ro, rl = None, 0.0
             else:
                 ro, rl = _f(self.boxes[0]), float(self.boxes[1])
-            check(lib().rtb_scene_create(self.tris.ctypes.data, len(self.tris), ro, rl, C.byref(h)), "rtb_scene_create")
+            if self.spheres is not None and len(self.spheres):
+                check(lib().rtb_scene_create_ext(self.tris.ctypes.data, len(self.tris), self.spheres.ctypes.data,
+                                                 len(self.spheres), ro, rl, C.byref(h)), "rtb_scene_create_ext")
+            else:
+                check(lib().rtb_scene_create(self.tris.ctypes.data, len(self.tris), ro, rl, C.byref(h)), "rtb_scene_create")
             self._h = h
+            if self.light is not None:
+                self.set_light(*self.light)
         return self._h
+
+    def set_light(self, orig, len2=0.0):
+        """`lights = Some(LightSource{orig, len2})` (raytrace.rs:594-597); orig None removes it."""
+        self.light = None if orig is None else (tuple(float(x) for x in orig), float(len2))
+        if self._h is not None:
+            check(lib().rtb_scene_set_light(self._h, None if orig is None else _f(orig), float(len2)), "rtb_scene_set_light")
 
     def info(self) -> RtbSceneInfo:
         out = RtbSceneInfo()
@@ -237,6 +252,34 @@ class Scene:
             self.release()
         except Exception:
             pass
+
+
+def analytic_sphere(orig, r, surface: SurfaceKind):
+    """EXTENSION: one analytic sphere record (SPH_DTYPE) for Scene(spheres=...)."""
+    c = surface._c()
+    out = np.zeros(1, SPH_DTYPE)
+    out["center"][0] = [float(x) for x in orig]
+    out["radius"], out["kind"], out["alpha"], out["scattering"] = float(r), c.kind, c.alpha, c.scattering
+    out["color"][0] = c.color[:]
+    return out
+
+
+def circles_scene(n=64, seed=1, light=((6.0, -1.0, 2.0), 0.6)) -> "Scene":
+    """BASELINE config 1 ("circles scene at 2K, primary + shadow rays"), defined by this build because the mounted
+    reference has none: n analytic spheres of random colour (one in eight a mirror, one in eight matte)
+    over a matte ground disk, one cube light."""
+    rng = np.random.RandomState(seed)
+    parts = []
+    for k in range(n):
+        c = [float(rng.uniform(-0.5, 3.5)), float(rng.uniform(-5.0, 5.0)), float(rng.uniform(4.0, 14.0))]
+        col = make_color(tuple(int(x) for x in rng.randint(30, 255, 3)))
+        surf = (SurfaceKind.Reflective(0.0, col, 0.6) if k % 8 == 0 else
+                SurfaceKind.Matte(col, 0.3) if k % 8 == 1 else SurfaceKind.Solid(col))
+        parts.append(analytic_sphere(c, float(rng.uniform(0.25, 0.7)), surf))
+    ground = make_disk([-1.5, 0.0, 9.0], unit([1.0, 0.0, 0.05]), 9.0, 0.1, 40,
+                       SurfaceKind.Matte(make_color((150, 150, 150)), 0.25), SurfaceKind.Solid([0.1, 0.1, 0.1]), -1.0)
+    return Scene(np.concatenate([make_dummy_triangle(), ground]), boxes=((0.0, 0.0, 20.1), 20.0),
+                 spheres=np.concatenate(parts), light=light)
 
 
 # ---------------------------------------------------------------------------

@@ -428,3 +428,70 @@ def test_render_rgb8_is_the_quantised_frame(R, O, scenes, tmp_path):
     path = str(tmp_path / "frame.png")
     R.write_png(path, (w, h), rgb)
     assert np.array_equal(decode_png(path)[2], want)
+
+
+# ---------------------------------------------------------------------------
+# EXTENSION: shadow rays and analytic spheres, oracle-vs-GPU
+# ---------------------------------------------------------------------------
+def _oracle_ext(O, scene, accel):
+    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), accel)
+    if scene.spheres is not None:
+        osc.add_spheres(scene.spheres.view(O.SPH_DTYPE))
+    if scene.light is not None:
+        osc.set_light(*scene.light)
+    return osc
+
+
+@pytest.mark.parametrize("det", [True, False])
+def test_shadow_rays_on_the_teapot_scene(R, O, det):
+    """main.rs's scene with `lights = Some(..)`: the shadow block of color_ray (commented out at raytrace.rs:1203-1224)
+    live on the GPU and in the oracle — ids, t, RGBA and the ray count (shadow rays are not `Rays`) bit-exact; the
+    reference-algorithm oracle (octree) and the oracle BVH agree with each other as well."""
+    s = R.main_scene(deterministic=det)
+    s.set_light((6.0, -2.0, 0.0), 0.5)
+    v, ov = R.main_viewport(480, 270, 5, 1), O.main_viewport(480, 270, 5, 1)
+    got = gpu_render(R, s, v, seed=6)
+    want = _oracle_ext(O, s, O.ACCEL_BVH).render(ov, seed=6)
+    assert_bit_exact(got, want, "teapot + light")
+    unlit = gpu_render(R, R.main_scene(deterministic=det), v, seed=6)
+    assert (bits(unlit[0]) != bits(got[0])).any(-1).sum() > 1000       # the light does something
+    assert np.array_equal(unlit[1], got[1])                              # ... but not to the primary hits
+    v2, ov2 = R.main_viewport(160, 90, 5, 1), O.main_viewport(160, 90, 5, 1)
+    assert_bit_exact(gpu_render(R, s, v2, seed=6), _oracle_ext(O, s, O.ACCEL_OCTREE).render(ov2, seed=6), "teapot + light, octree oracle")
+    s.set_light(None)                                                    # back to the reference's live integrator
+    again = gpu_render(R, s, v, seed=6)
+    assert np.array_equal(bits(again[0]), bits(unlit[0]))
+    s.release()
+
+
+@pytest.mark.parametrize("spp,light", [(1, True), (1, False), (3, True)])
+def test_circles_scene_analytic_spheres(R, O, spp, light):
+    """BASELINE config 1: analytic spheres (Solid / Matte / mirror) over a ground disk, primary + shadow rays + bounces,
+    against the oracle; sphere ids follow the triangles'."""
+    s = R.circles_scene(n=24, seed=3)
+    if not light:
+        s.light = None
+    w, h = (512, 288) if spp == 1 else (200, 113)
+    v, ov = R.main_viewport(w, h, 3, spp), O.main_viewport(w, h, 3, spp)
+    got = gpu_render(R, s, v, seed=9)
+    assert_bit_exact(got, _oracle_ext(O, s, O.ACCEL_BVH).render(ov, seed=9), "circles")
+    ids = np.unique(got[1])
+    assert ids.max() >= len(s.tris) and ids.max() < len(s.tris) + 24 and (ids >= len(s.tris)).sum() >= 10
+    s.release()
+
+
+def test_sphere_edge_cases(R, O):
+    """Camera inside a sphere (far root, back face), a sphere behind the camera (both roots negative), touching
+    spheres, a huge sphere around everything; 2K-wide band to cover the config's resolution."""
+    col = R.make_color((200, 100, 50))
+    sph = np.concatenate([
+        R.analytic_sphere([2.0, 0.0, 0.0], 1.5, R.SurfaceKind.Matte(col, 0.4)),          # contains the camera plane
+        R.analytic_sphere([2.0, 0.0, -5.0], 1.0, R.SurfaceKind.Solid(col)),              # behind
+        R.analytic_sphere([2.0, -1.0, 6.0], 1.0, R.SurfaceKind.Reflective(0.0, col, 0.5)),
+        R.analytic_sphere([2.0, 1.0, 6.0], 1.0, R.SurfaceKind.Reflective(0.01, col, 0.5)),   # touches the previous one
+        R.analytic_sphere([0.0, 0.0, 0.0], 19.0, R.SurfaceKind.Solid(R.make_color((10, 20, 30)))),
+    ])
+    s = R.Scene(R.make_dummy_triangle(), boxes=None, spheres=sph, light=((3.0, 0.0, 3.0), 0.2))
+    v, ov = R.main_viewport(2560, 64, 4, 1), O.main_viewport(2560, 64, 4, 1)
+    assert_bit_exact(gpu_render(R, s, v, seed=2), _oracle_ext(O, s, O.ACCEL_BVH).render(ov, seed=2), "sphere edge cases")
+    s.release()

@@ -36,9 +36,10 @@ def test_struct_sizes_match_the_header(R, tmp_path):
 #include "rtb.h"
 #include "rtb_host.h"
 int main(void) {
-    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(RtbTriangle), sizeof(RtbView), sizeof(RtbStats), sizeof(RtbSceneInfo),
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu ", sizeof(RtbTriangle), sizeof(RtbView), sizeof(RtbStats), sizeof(RtbSceneInfo),
            sizeof(RtbSurface), offsetof(RtbView, seed), offsetof(RtbStats, ms_stage), offsetof(RtbSceneInfo, ms_upload),
            sizeof(RtbMeshInstance), offsetof(RtbMeshInstance, kind), offsetof(RtbSceneInfo, n_refs));
+    printf("%zu %zu\\n", sizeof(RtbSphere), offsetof(RtbSphere, kind));
     return 0;
 }''')
     exe = tmp_path / "sizes"
@@ -46,7 +47,8 @@ int main(void) {
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [_lib.TRI_DTYPE.itemsize, C.sizeof(_lib.RtbView), C.sizeof(_lib.RtbStats), C.sizeof(_lib.RtbSceneInfo),
             C.sizeof(_lib.RtbSurface), _lib.RtbView.seed.offset, _lib.RtbStats.ms_stage.offset, _lib.RtbSceneInfo.ms_upload.offset,
-            C.sizeof(_lib.RtbMeshInstance), _lib.RtbMeshInstance.kind.offset, _lib.RtbSceneInfo.n_refs.offset]
+            C.sizeof(_lib.RtbMeshInstance), _lib.RtbMeshInstance.kind.offset, _lib.RtbSceneInfo.n_refs.offset,
+            _lib.SPH_DTYPE.itemsize, _lib.SPH_DTYPE.fields["kind"][1]]
     assert got == want, (got, want)
     assert got[0] == 140 and got[1] == 88
 
