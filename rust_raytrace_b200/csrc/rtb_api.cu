@@ -241,7 +241,20 @@ int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d
     // Piece boundaries.  With copies to overlap (taper) the pieces shrink linearly, first : last = (pieces+1) : 2, so the
     // copy of the last piece — the one nothing can hide — is short.
     static const bool taper_on = getenv("RTB_PIECE_TAPER") ? atoi(getenv("RTB_PIECE_TAPER")) != 0 : true;
+    // experiment knob: explicit relative piece sizes, "RTB_PIECE_WEIGHTS=1,3,4,4,2,1" (also sets the piece count)
+    static const std::vector<double> weights = [] {
+        std::vector<double> w;
+        if (const char* e = getenv("RTB_PIECE_WEIGHTS"))
+            for (const char* p = e; *p;) { char* end; const double x = strtod(p, &end); if (end == p) break; if (x > 0) w.push_back(x); p = *end ? end + 1 : end; }
+        return w;
+    }();
+    if (taper && weights.size() >= 2) pieces = std::min<uint32_t>((uint32_t)std::min<size_t>(weights.size(), RTB_MAX_CHUNKS), whole.my_tile_rows);
     auto bound = [&](uint32_t c) -> uint32_t {        // first band of piece c (relative), bound(pieces) = all bands
+        if (taper && weights.size() >= 2) {
+            double tot = 0, acc = 0;
+            for (uint32_t i = 0; i < pieces; ++i) { tot += weights[i]; if (i < c) acc += weights[i]; }
+            return c >= pieces ? whole.my_tile_rows : (uint32_t)((double)whole.my_tile_rows * acc / tot);
+        }
         if (!taper || !taper_on || pieces < 3) return (uint32_t)((uint64_t)whole.my_tile_rows * c / pieces);
         const uint64_t total_w = (uint64_t)pieces * (pieces + 3) / 2;                 // sum of (pieces + 1 - i), i < pieces
         const uint64_t w = (uint64_t)c * (2 * pieces + 3 - c) / 2;                    // sum over i < c

@@ -33,6 +33,7 @@ constexpr uint32_t LEAF_FLAG = 0x80000000u;
 constexpr int WF_BLOCK = 128;           // threads per CTA of the persistent kernels
 constexpr int WF_OVF = 3 * (RTB_STACK / 2 + 1) + 2;   // worst-case BVH4 stack (tree height < RTB_STACK), thread-local overflow part
 constexpr int WF_SMEM_STACK = 8;        // stack entries per thread kept in shared memory
+constexpr uint32_t WF_SENTINEL = 0x7fffffffu;   // bottom of a whole-in-shared-memory stack (never a node index: < 2^31 nodes)
 #ifndef WF_TRACE_MIN_BLOCKS
 #define WF_TRACE_MIN_BLOCKS 4
 #endif
@@ -100,7 +101,7 @@ __device__ __forceinline__ uint32_t root_code_of(const SceneDev&) {
     return 0u;   // BVH4 node 0 (an empty scene has one node whose four slots are all empty)
 }
 
-__device__ __forceinline__ void start_ray(TravState& s, V3 o, V3 d, uint32_t root_code) {
+__device__ __forceinline__ void start_ray(TravState& s, V3 o, V3 d, uint32_t root_code, int sp0 = 0) {
     s.o = o; s.d = d;
     // |1/d| clamped so a zero direction component gives +-huge, not inf (inf - inf = NaN in the fused slab test)
     s.ix = fminf(fmaxf(1.0f / d.x, -1e30f), 1e30f);
@@ -109,7 +110,7 @@ __device__ __forceinline__ void start_ray(TravState& s, V3 o, V3 d, uint32_t roo
     s.ox = -o.x * s.ix; s.oy = -o.y * s.iy; s.oz = -o.z * s.iz;
     s.tbest = FLT_MAX;
     s.h.t = FLT_MAX; s.h.slot = -1; s.h.orig = 0xffffffffu;
-    s.sp = 0;
+    s.sp = sp0;
     s.cur = root_code;
 }
 
@@ -133,9 +134,10 @@ __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, boo
     // of each SM's 256 KB and grows with the tree height (a 1 M-triangle scene would drop to 4 CTAs/SM).  Measured on
     // B200, 4K teapot frame: 40 entries 3.22 ms, 16: 3.21, 12: 3.20, 8: 3.18, 6: 3.15, 4: 3.16 — L1 capacity is not the limiter.
     auto pop = [&]() {
+        if (!OVF) { --s.sp; s.cur = stack[s.sp * WF_BLOCK]; trav = s.cur != WF_SENTINEL; return; }
         if (s.sp == 0) { trav = false; return; }
         --s.sp;
-        s.cur = (!OVF || s.sp < smem_depth) ? stack[s.sp * WF_BLOCK] : ovf[s.sp - smem_depth];
+        s.cur = (s.sp < smem_depth) ? stack[s.sp * WF_BLOCK] : ovf[s.sp - smem_depth];
     };
     auto push = [&](uint32_t code) {
         if (!OVF || s.sp < smem_depth) stack[s.sp * WF_BLOCK] = code; else ovf[s.sp - smem_depth] = code;
@@ -179,7 +181,18 @@ __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, boo
         }
         RTB_CE(0, 1) RTB_CE(2, 3) RTB_CE(0, 2) RTB_CE(1, 3) RTB_CE(1, 2)
 #undef RTB_CE
-        if (key[0] == INF) {
+        if (!OVF) {
+            // whole stack in shared memory, entry 0 = WF_SENTINEL: no branches — the three far children are stored
+            // unconditionally (a store above the top is harmless), the top only moves past the ones that were hit,
+            // and a pop that reaches the sentinel ends the ray
+            stack[s.sp * WF_BLOCK] = code[3]; s.sp += (key[3] < INF) ? 1 : 0;
+            stack[s.sp * WF_BLOCK] = code[2]; s.sp += (key[2] < INF) ? 1 : 0;
+            stack[s.sp * WF_BLOCK] = code[1]; s.sp += (key[1] < INF) ? 1 : 0;
+            const bool miss = key[0] == INF;
+            s.sp -= miss ? 1 : 0;
+            s.cur = miss ? stack[s.sp * WF_BLOCK] : code[0];
+            trav = s.cur != WF_SENTINEL;
+        } else if (key[0] == INF) {
             pop();
         } else {
             s.cur = code[0];                                   // nearest first, the rest far-to-near on the stack
@@ -262,7 +275,9 @@ k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
     bool trav = false;
     uint32_t ray_id = 0;
     TravState s;
-    start_ray(s, mk(0.f, 0.f, 0.f), mk(1.f, 1.f, 1.f), root_code);
+    constexpr int SP0 = OVF ? 0 : 1;         // !OVF: stack entry 0 holds the sentinel
+    if (!OVF) stack[0] = WF_SENTINEL;
+    start_ray(s, mk(0.f, 0.f, 0.f), mk(1.f, 1.f, 1.f), root_code, SP0);
     unsigned long long n_node = 0, n_tri = 0;
 
     for (;;) {
@@ -273,7 +288,7 @@ k_wf_trace(const SceneDev sc, const ViewDev vw, uint32_t smp, uint32_t n,
                 V3 o, d; Rng g; Pixel px;
                 if (primary_ray(vw, idx, smp, &o, &d, &g, &px)) {   // slots outside the image have no ray
                     ray_id = idx;
-                    start_ray(s, o, d, root_code);
+                    start_ray(s, o, d, root_code, SP0);
                     trav = true;
                 }
             }
@@ -426,7 +441,9 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
     uint32_t slot = 0, level = 0;
     Rng g; g.state = 0;
     TravState s;
-    start_ray(s, mk(0.f, 0.f, 0.f), mk(1.f, 1.f, 1.f), root_code);
+    constexpr int SP0 = OVF ? 0 : 1;         // !OVF: stack entry 0 holds the sentinel
+    if (!OVF) stack[0] = WF_SENTINEL;
+    start_ray(s, mk(0.f, 0.f, 0.f), mk(1.f, 1.f, 1.f), root_code, SP0);
     unsigned long long n_node = 0, n_tri = 0, n_rays = 0;
 
     for (;;) {
@@ -448,7 +465,7 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
                         pb.stack[(size_t)level * pb.n_slots + slot] = make_float4(color.x, color.y, color.z, alpha);
                         ++level;
                         if (level < vw.maxdepth) {          // project_ray(depth-1) with depth-1 > 0
-                            start_ray(s, no, nd, root_code);
+                            start_ray(s, no, nd, root_code, SP0);
                             trav = true; ended = false; ++n_rays;
                         }                                   // else depth 0: black (:1261), not counted
                     }
@@ -462,7 +479,7 @@ k_wf_bounce(const SceneDev sc, const ViewDev vw, const PathBuffers pb, const flo
                 slot = __float_as_uint(ro.w);
                 level = 1u;
                 g.state = pb.rng_state[slot];
-                start_ray(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), root_code);
+                start_ray(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), root_code, SP0);
                 has_path = true; trav = true; ++n_rays;
             }
         }
@@ -850,8 +867,9 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
     // persistent grids: as many CTAs as fit, given the shared-memory traversal stacks (3 entries per BVH4 level, 4 B each, per thread)
     const bool stats = (vw.flags & RTB_FLAG_STATS) != 0;
     // the whole worst-case stack in shared memory when 8 CTAs of it fit an SM (<= 24 KB per CTA), else 8 entries + overflow
-    const bool ovf = env.smem_stack > 0 || (size_t)sc.stack4 * WF_BLOCK * sizeof(uint32_t) > 24u * 1024u;
-    const int smem_depth = ovf ? std::min<int>((int)sc.stack4, env.smem_stack > 0 ? env.smem_stack : WF_SMEM_STACK) : (int)sc.stack4;
+    // (whole stack = worst case + the sentinel entry + the one entry above the top the branch-free pushes may touch)
+    const bool ovf = env.smem_stack > 0 || (size_t)(sc.stack4 + 2u) * WF_BLOCK * sizeof(uint32_t) > 24u * 1024u;
+    const int smem_depth = ovf ? std::min<int>((int)sc.stack4, env.smem_stack > 0 ? env.smem_stack : WF_SMEM_STACK) : (int)sc.stack4 + 2;
     const size_t smem = (size_t)smem_depth * WF_BLOCK * sizeof(uint32_t);
     int dev = 0, sms = 0, per_sm_t = 0, per_sm_b = 0;
     RTB_CUDA(cudaGetDevice(&dev));

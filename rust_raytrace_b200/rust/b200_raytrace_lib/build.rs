@@ -19,7 +19,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
 
-    let units = ["rtb_api.cu", "rtb_lbvh.cu", "rtb_trace.cu", "rtb_wavefront.cu", "host/raytrace_host.cpp"];
+    let units = ["rtb_api.cu", "rtb_lbvh.cu", "rtb_scene.cu", "rtb_ext.cu", "rtb_trace.cu", "rtb_wavefront.cu", "host/raytrace_host.cpp"];
     let mut objs = Vec::new();
     for u in units {
         let src = csrc.join(u);

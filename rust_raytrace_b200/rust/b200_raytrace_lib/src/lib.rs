@@ -92,6 +92,9 @@ extern "C" {
                   t_out: *mut f32, stats: *mut RtbStats) -> c_int;
     fn rtb_render_progressive(s: *mut RtbSceneOpaque, view: *const RtbView, rgba_out: *mut f32,
                               stats: *mut RtbStats) -> c_int;
+    fn rtb_render_rgb8(s: *mut RtbSceneOpaque, view: *const RtbView, rgb_out: *mut u8, stats: *mut RtbStats) -> c_int;
+    fn rtb_scene_set_light(s: *mut RtbSceneOpaque, orig: *const f32, len2: f32) -> c_int;
+    fn rtbh_write_png_rgb8(path: *const c_char, width: u32, height: u32, rgb: *const u8) -> c_int;
     fn rtb_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
     fn rtb_host_unregister(ptr: *mut c_void) -> c_int;
 }
@@ -182,6 +185,9 @@ pub struct B200RayCaster {
     pub seed: u64,
     /// samples of a multi-spp frame are partitioned over the GPUs and reduced over NVLink (rtb_render_progressive)
     pub progressive: bool,
+    /// EXTENSION: `LightSource {orig, len2}` (raytrace.rs:594-597) — turns the commented-out shadow block of color_ray
+    /// (raytrace.rs:1203-1224) on; the current `Scene` has no `lights` field to carry it
+    pub light: Option<([f32; 3], f32)>,
     cache: Mutex<Option<Uploaded>>,
     /// (address, bytes) of the caller's image buffer currently pinned with rtb_host_register: pinning 133 MB costs
     /// milliseconds, so it is done once per buffer, not once per frame
@@ -193,7 +199,7 @@ unsafe impl Sync for B200RayCaster {}
 
 impl B200RayCaster {
     pub fn new() -> Self {
-        B200RayCaster { seed: 0, progressive: false, cache: Mutex::new(None), pinned: Mutex::new(None) }
+        B200RayCaster { seed: 0, progressive: false, light: None, cache: Mutex::new(None), pinned: Mutex::new(None) }
     }
 
     fn scene_handle(&self, s: &Scene, n_gpus: usize) -> Result<*mut RtbSceneOpaque, String> {
@@ -223,6 +229,32 @@ impl B200RayCaster {
 }
 
 impl B200RayCaster {
+    fn apply_light(&self, h: *mut RtbSceneOpaque) {
+        match self.light {
+            Some((o, len2)) => unsafe { rtb_scene_set_light(h, o.as_ptr(), len2) },
+            None => unsafe { rtb_scene_set_light(h, std::ptr::null(), 0.0) },
+        };
+    }
+
+    /// main.rs:191-227 in one call: the frame of `walk_rays` quantised on the GPU with write_png's `(c * 255.) as u8`
+    /// (raytrace.rs:1468-1473), 3 bytes per pixel over PCIe instead of 16, written as an 8-bit RGB PNG.
+    /// Returns the number of rays (the reference's "Rays" stat).
+    pub fn render_png(&self, v: &Viewport, s: &Scene, n_gpus: usize, path: &str) -> Result<u64, String> {
+        let h = self.scene_handle(s, n_gpus)?;
+        self.apply_light(h);
+        let view = view_from_viewport(v, self.seed);
+        let mut rgb = vec![0u8; v.width * v.height * 3];
+        let mut st = RtbStats::default();
+        if unsafe { rtb_render_rgb8(h, &view, rgb.as_mut_ptr(), &mut st) } != 0 {
+            return Err(last_error());
+        }
+        let cpath = std::ffi::CString::new(path).map_err(|e| e.to_string())?;
+        if unsafe { rtbh_write_png_rgb8(cpath.as_ptr(), v.width as u32, v.height as u32, rgb.as_ptr()) } != 0 {
+            return Err(format!("cannot write {}", path));
+        }
+        Ok(st.rays)
+    }
+
     fn pin(&self, ptr: *mut c_void, bytes: usize) {
         let mut p = self.pinned.lock().unwrap();
         if *p == Some((ptr as usize, bytes)) {
@@ -254,6 +286,7 @@ impl RayCaster for B200RayCaster {
         assert_eq!(data.len(), v.width * v.height);
         assert_eq!(std::mem::size_of::<Color>(), 16);
         let h = self.scene_handle(s, threads).unwrap_or_else(|e| panic!("b200: {}", e));
+        self.apply_light(h);
         let view = view_from_viewport(v, self.seed);
         let mut st = RtbStats::default();
         let bytes = data.len() * 16;
