@@ -56,7 +56,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_wf_bounce launch of the teapot4k frame at N=1, from the
 # `ncu --set full` capture summarised in profiles/ (see DESIGN.md "Roofline"); null for every other configuration.
-NCU_TRAFFIC_BOUNCE_TEAPOT4K = 370.4e6   # profiles/r1_v6_k_wf_bounce_raw.csv: 257.6 MB read + 112.8 MB written
+NCU_TRAFFIC_BOUNCE_TEAPOT4K = 370.1e6   # profiles/r1_v7_k_wf_bounce_raw.csv: 257.6 MB read + 112.5 MB written
 
 
 def measured_peaks():
@@ -239,6 +239,8 @@ def run_gpu(args):
     dev_ids = (C.c_int * 1)(local_rank)
     _lib.check(L.rtb_init(1, dev_ids), "rtb_init")
     scene = build_scene(R, name)
+    h = scene.upload()
+    scene.release()                 # the first build of a process pays CUDA's lazy kernel loading: report the second
     h = scene.upload()
     info = scene.info()
     view = R.main_viewport(W, H, maxdepth, spp)

@@ -718,11 +718,14 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
                       bool force_karras, BuildResult* out) {
     *out = BuildResult();
     // device time of the build = the bounds/split phase (s0..s1) + everything after the allocations (e0..e1)
-    cudaEvent_t e0, e1, s0, s1;
+    cudaEvent_t e0, e1, s0, s1, s2, s3;
     RTB_CUDA(cudaEventCreate(&e0));
     RTB_CUDA(cudaEventCreate(&e1));
     RTB_CUDA(cudaEventCreate(&s0));
     RTB_CUDA(cudaEventCreate(&s1));
+    RTB_CUDA(cudaEventCreate(&s2));
+    RTB_CUDA(cudaEventCreate(&s3));
+    bool split_emitted = false;
     const uint32_t B = 256;
     uint32_t launches = 0;
 
@@ -765,13 +768,17 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
             RTB_CUDA(cudaMemsetAsync(cnt.p + n, 0, sizeof(uint32_t), stream));
             launches += (uint32_t)rtbsort::exclusive_sum<uint32_t>(cnt.p, off.p, n + 1, scan_tmp.p, stream);
             uint32_t n_refs = n;
+            RTB_CUDA(cudaEventRecord(s1, stream));
             RTB_CUDA(cudaMemcpyAsync(&n_refs, off.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             RTB_CUDA(cudaStreamSynchronize(stream));
             if (n_refs > n) {
                 DevBuf<float4> rlo, rhi;
                 RTB_CUDA(rlo.alloc(n_refs)); RTB_CUDA(rhi.alloc(n_refs)); RTB_CUDA(ref_keep.alloc(n_refs));
+                RTB_CUDA(cudaEventRecord(s2, stream));
+                split_emitted = true;
                 k_split_refs<true><<<cdiv(n, B), B, 0, stream>>>(d_tris, d_keep, n, plo.p, phi.p, scratch.p, inv_div, nullptr,
                                                                  off.p, rlo.p, rhi.p, ref_keep.p); ++launches;
+                RTB_CUDA(cudaEventRecord(s3, stream));
                 RTB_CUDA(cudaStreamSynchronize(stream));      // the old boxes are freed at the end of this scope
                 std::swap(plo.p, rlo.p); std::swap(phi.p, rhi.p);
                 d_keep = ref_keep.p;
@@ -781,7 +788,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         }
     }
 
-    RTB_CUDA(cudaEventRecord(s1, stream));
+    if (!(n > 0 && benv.split_div > 0)) RTB_CUDA(cudaEventRecord(s1, stream));
 
     // final arrays (owned by the scene afterwards)
     const uint32_t n_alloc = n ? n : 1;
@@ -805,7 +812,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaMemcpyAsync(out->d_nodes4, h4, sizeof h4, cudaMemcpyHostToDevice, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
         out->n_nodes4 = 1;
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1); cudaEventDestroy(s2); cudaEventDestroy(s3);
         return RTB_OK;
     }
 
@@ -932,11 +939,12 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     RTB_CUDA(cudaMemcpyAsync(&h, scratch.p, sizeof h, cudaMemcpyDeviceToHost, stream));
     RTB_CUDA(cudaStreamSynchronize(stream));
     RTB_CUDA(cudaGetLastError());
-    float ms_split = 0.f;
+    float ms_split = 0.f, ms_emit = 0.f;
     RTB_CUDA(cudaEventElapsedTime(&out->ms_build, e0, e1));
     RTB_CUDA(cudaEventElapsedTime(&ms_split, s0, s1));
-    out->ms_build += ms_split;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1);
+    if (split_emitted) RTB_CUDA(cudaEventElapsedTime(&ms_emit, s2, s3));
+    out->ms_build += ms_split + ms_emit;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1); cudaEventDestroy(s2); cudaEventDestroy(s3);
 
     auto dec = [](uint32_t o) { uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; float f; memcpy(&f, &u, 4); return f; };
     for (int k = 0; k < 3; ++k) { out->lo[k] = dec(h.scene_lo[k]); out->hi[k] = dec(h.scene_hi[k]); }

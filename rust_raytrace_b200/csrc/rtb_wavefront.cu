@@ -150,9 +150,9 @@ __device__ __forceinline__ void trav_round(const SceneDev& sc, TravState& s, boo
         if (!go) continue;
         // one BVH4 node = one 128-byte line: 4 child boxes (SoA) + 4 child codes
         const float4* np = sc.nodes4 + 8u * s.cur;
-        const float4 lx = __ldg(np + 0), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3);
-        const float4 lz = __ldg(np + 4), hz = __ldg(np + 5);
-        const uint4 cd = __ldg(reinterpret_cast<const uint4*>(np + 6));
+        float4 lx, hx, ly, hy, lz, hz, cdf, pad_;
+        ldg256(np + 0, lx, hx); ldg256(np + 2, ly, hy); ldg256(np + 4, lz, hz); ldg256(np + 6, cdf, pad_);
+        const uint4 cd = make_uint4(__float_as_uint(cdf.x), __float_as_uint(cdf.y), __float_as_uint(cdf.z), __float_as_uint(cdf.w));
         if (STATS) n_node += 4;
         const float INF = __int_as_float(0x7f800000);
         float key[4];
