@@ -495,3 +495,23 @@ def test_sphere_edge_cases(R, O):
     v, ov = R.main_viewport(2560, 64, 4, 1), O.main_viewport(2560, 64, 4, 1)
     assert_bit_exact(gpu_render(R, s, v, seed=2), _oracle_ext(O, s, O.ACCEL_BVH).render(ov, seed=2), "sphere edge cases")
     s.release()
+
+
+@pytest.mark.parametrize("extra", [[], ["--instanced", "--rgb8"]])
+def test_main_rs_equivalent_driver(R, O, scenes, tmp_path, extra):
+    """raytrace_b200 (csrc/host/raytrace_main.cpp) does what main.rs:116-227 does — scene, camera, walk_rays, print_stats,
+    write_png — over the C ABI: its PNG must hold the oracle's frame through the oracle's quantiser, its "Rays" line the
+    oracle's ray count."""
+    import os
+    import subprocess
+    from png_util import decode_png
+    from rust_raytrace_b200 import _lib
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "raytrace_b200")
+    out = str(tmp_path / "test.png")
+    r = subprocess.run([exe, "--mesh", R.raytrace.TEAPOT_MESH, "--size", "320x180", "--out", out, "--seed", "11"] + extra,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rgba, _, _, st = scenes[False][2].render(O.main_viewport(320, 180, 5, 1), seed=11)
+    w, h, px = decode_png(out)
+    assert (w, h) == (320, 180) and np.array_equal(px, O.quantize_rgb8(rgba.reshape(-1, 4)).reshape(180, 320, 3))
+    assert f"Rays: {st.rays}" in r.stdout and "million rays/s" in r.stdout

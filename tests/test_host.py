@@ -176,3 +176,18 @@ def test_write_png_holds_the_reference_quantisation(R, O, wh, tmp_path):
         gw, gh, px = decode_png(p)
         assert (gw, gh) == (w, h) and np.array_equal(px, want)
     assert open(p1, "rb").read() == open(p2, "rb").read()
+
+
+def test_driver_binary_fails_loudly_without_a_device(R):
+    """raytrace_b200, the main.rs-equivalent driver: built by the Makefile, exits non-zero with the library's message
+    when there is no GPU (no CPU rendering path)."""
+    import os
+    import subprocess
+    import torch
+    from rust_raytrace_b200 import _lib
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "raytrace_b200")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, "--mesh", R.raytrace.TEAPOT_MESH], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
