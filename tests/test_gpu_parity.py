@@ -515,3 +515,14 @@ def test_main_rs_equivalent_driver(R, O, scenes, tmp_path, extra):
     w, h, px = decode_png(out)
     assert (w, h) == (320, 180) and np.array_equal(px, O.quantize_rgb8(rgba.reshape(-1, 4)).reshape(180, 320, 3))
     assert f"Rays: {st.rays}" in r.stdout and "million rays/s" in r.stdout
+
+
+def test_circles_2k_full_size(R, O):
+    """BASELINE config 1 at its own size: 64 analytic spheres + ground disk + light, 2560x1440, maxdepth 2 (primary + one
+    bounce) + one shadow ray per hit — every pixel against the oracle (bench.py's `circles2k` workload)."""
+    s = R.circles_scene()
+    v, ov = R.main_viewport(2560, 1440, 2, 1), O.main_viewport(2560, 1440, 2, 1)
+    got = gpu_render(R, s, v, seed=7)
+    assert_bit_exact(got, _oracle_ext(O, s, O.ACCEL_BVH).render(ov, seed=7), "circles 2K")
+    assert (got[1] >= len(s.tris)).mean() > 0.05          # spheres cover a good part of the frame
+    s.release()

@@ -7,7 +7,8 @@ from rust_raytrace_b200 import _lib
 L = _lib.lib()
 _lib.check(L.rtb_init(1, None), "init")
 scene = R.main_scene(False); h = scene.upload()
-v = R.main_viewport(3840, 2160, 5, 1); v.seed = 7; v.flags = _lib.RTB_FLAG_TIMING
+MD = int(os.environ.get("MAXDEPTH", "5"))
+v = R.main_viewport(3840, 2160, MD, 1); v.seed = 7; v.flags = _lib.RTB_FLAG_TIMING
 d = torch.zeros((2160, 3840, 4), dtype=torch.float32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
