@@ -7,7 +7,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 V=$ROOT/rust_raytrace_b200/csrc/build/variants
 mkdir -p $V/obj_$NAME
 cd $ROOT/rust_raytrace_b200/csrc
-for f in rtb_api rtb_lbvh rtb_trace rtb_wavefront; do
+for f in rtb_api rtb_lbvh rtb_scene rtb_ext rtb_trace rtb_wavefront; do
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math \
        -I$ROOT/include -I. $FLAGS -c $f.cu -o $V/obj_$NAME/$f.o &
 done
