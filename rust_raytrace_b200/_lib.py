@@ -107,7 +107,7 @@ class RtbMeshInstance(C.Structure):
                 ("scattering", C.c_float)]
 
 
-# Every symbol include/rtb.h and include/rtb_host.h declare (checked by tests/test_abi.py).
+# Every symbol include/rtb.h and include/rtb_host.h declare (checked by tests/test_host.py::test_library_exports_every_declared_symbol).
 RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render_rgb8", "rtb_scene_create_instanced", "rtb_assemble_triangles",

@@ -22,3 +22,20 @@ print("progressive ok", float(data.mean()))
 print("quantise", R.quantize_rgb8(data).shape)
 _lib.check(_lib.lib().rtb_selftest_sort(5000, 63, 9), "sort")
 print("sanitize workload done")
+# second half of round 1: scene assembly + cull kernels, reference splitting, rgb8 output, extension renderer
+from rust_raytrace_b200 import raytrace as rt
+si = R.main_scene(False, instanced=True)
+v = R.main_viewport(48, 40, 5, 1)
+rgb = np.zeros((40, 48, 3), np.uint8)
+R.B200RayCaster(seed=3).walk_rays_rgb8(v, si, rgb)
+print("instanced + rgb8 ok", int(rgb.sum()), "refs", si.info().n_refs, flush=True)
+print("cull", len(rt.cull_triangles(s.tris, ((0.0, 0.5, 5.0), 1.0))))
+c = R.circles_scene(n=8, seed=2)
+for spp in (1, 2):
+    vv = R.main_viewport(48, 40, 3, spp)
+    d = R.new_image(vv)
+    print("circles spp", spp, R.B200RayCaster(want_ids=True, seed=3).walk_rays(vv, c, d, threads=1).total_rays, flush=True)
+s.set_light((6.0, -2.0, 0.0), 0.5)
+d = R.new_image(v)
+print("teapot + light", R.B200RayCaster(seed=3).walk_rays(v, s, d, threads=1).total_rays)
+print("sanitize workload (part 2) done")
