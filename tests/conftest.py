@@ -26,7 +26,7 @@ def R():
     """The product package; builds librtb.so if it is missing (nvcc cross-compiles without a GPU)."""
     from rust_raytrace_b200 import _lib
 
-    if not os.path.exists(_lib.LIB_PATH):
+    if not os.path.exists(_lib.LIB_PATH) or not os.path.exists(os.path.join(os.path.dirname(_lib.LIB_PATH), "raytrace_b200")):
         _lib.build()
     import rust_raytrace_b200
 
