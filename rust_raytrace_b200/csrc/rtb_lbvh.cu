@@ -250,8 +250,8 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __re
 
 
 // ---------------------------------------------------------------------------------------------------------
-// PLOC — parallel locally-ordered clustering (Meister & Bittner 2018) on the Morton-sorted primitives: the
-// default topology builder.  Clusters sit in Morton order; every cluster looks PLOC_R places left and right for the
+// PLOC — parallel locally-ordered clustering (Meister & Bittner 2018) on the Morton-sorted primitives
+// (RTB_BUILDER=ploc; the default of most of round 1, faster to build than the binned-SAH tree, 6-18 % slower to trace).  Clusters sit in Morton order; every cluster looks PLOC_R places left and right for the
 // neighbour whose union box has the smallest surface area; mutual nearest neighbours merge into a new node; the
 // array is compacted; repeat until one cluster is left.  Compared with the plain radix tree (k_hierarchy) the result
 // needs 14 % fewer BVH4 node visits per bounce ray on the teapot scene and 22-25 % fewer on the 1 M-triangle field
@@ -469,6 +469,209 @@ __global__ void k_ploc_finish(uint32_t n, const int2* __restrict__ pchildren, co
     if (kid == 0) parent[0] = -1;
     if (l < n) vals_out[off_l] = sorted_vals[l];
     if (r < n) vals_out[off_r] = sorted_vals[r];
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Binned-SAH top-down build (the default topology builder): the quality yardstick of tools/experiments/bvh_quality.cpp on
+// the GPU.  4K teapot frame 2.28 -> 2.13 ms, 1 M-triangle field 1.35 -> 1.11 ms against PLOC (RTB_BUILDER=ploc).
+// Breadth-first, one kernel per tree level, one WARP per node: centroid bounds -> 16 bins per axis (shared-memory
+// atomics) -> the 45 candidate planes evaluated by 45 lanes (cost = A(L) n_L + A(R) n_R) -> stable partition of the
+// node's reference range from one index buffer into the other (left block, then right block; n_L is known from the
+// bin counts) -> two children.  Splitting goes down to single references; the SAH leaf rule of k_node_kind then
+// collapses subtrees of <= RTB_LEAF_MAX as for the other builders.  Output is in the builder's node convention
+// (internal ids 0..n-2 handed out by an atomic counter with root 0, leaf id n-1+k for the reference at position k),
+// every node covers a contiguous range.  The top levels run on few warps (a 1 M-reference root is one warp looping
+// 31 K times), so this build takes longer than PLOC; it is not part of the frame time (main.rs:160 vs :191).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SAH_BINS = 16;
+constexpr int SAH_CAND = 3 * (SAH_BINS - 1);
+constexpr int SAH_BIG_TEAM = 512;        // threads per node for nodes of more than SAH_BIG references (one CTA each)
+constexpr uint32_t SAH_BIG = 2048;
+constexpr int SAH_WARPS = 4;             // small nodes: one warp each, this many per CTA
+struct SahItem { int node; uint32_t lo, hi; };     // references [lo, hi) of the level's input index buffer
+struct SahState { uint32_t n_next_small, n_next_big, next_internal, pad; };
+struct SahBins {
+    uint32_t cnt[3][SAH_BINS];
+    uint32_t lo[3][SAH_BINS][3], hi[3][SAH_BINS][3];     // ordered-uint encoded box per bin
+    float cost[SAH_CAND]; uint32_t nl[SAH_CAND];
+    float red[6][SAH_BIG_TEAM / 32];                      // cross-warp reduction of the centroid bounds
+    uint32_t wl[SAH_BIG_TEAM / 32], wr[SAH_BIG_TEAM / 32];
+    int best; uint32_t n_left;
+};
+
+__device__ __forceinline__ int sah_bin(float c, float cmin, float k) {     // k = SAH_BINS / extent
+    const int b = (int)((c - cmin) * k);
+    return b < 0 ? 0 : (b > SAH_BINS - 1 ? SAH_BINS - 1 : b);
+}
+
+// One node, split by a team of TEAM threads (a warp, or a whole CTA of SAH_BIG_TEAM threads for the big nodes near the root).
+template <int TEAM>
+__device__ void sah_split_node(const SahItem item, unsigned tid, SahBins& sb, const uint32_t* __restrict__ src,
+                               uint32_t* __restrict__ dst, const float4* __restrict__ plo, const float4* __restrict__ phi,
+                               uint32_t n, SahItem* __restrict__ next_small, SahItem* __restrict__ next_big, SahState* st,
+                               int2* __restrict__ children, int2* __restrict__ range, int* __restrict__ parent,
+                               uint32_t* __restrict__ leaf_vals) {
+    const unsigned FULLM = 0xffffffffu;
+    const unsigned lane = tid & 31u, wid = tid >> 5;
+    constexpr int NW = TEAM / 32;
+    auto team_sync = [&]() { if (TEAM == 32) __syncwarp(); else __syncthreads(); };
+    const uint32_t lo = item.lo, hi = item.hi, count = hi - lo;
+
+    // centroid bounds
+    float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (uint32_t i = lo + tid; i < hi; i += TEAM) {
+        const uint32_t r = src[i];
+        const float4 l = plo[r], h = phi[r];
+        const float c[3] = {0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z)};
+        for (int a = 0; a < 3; ++a) { cmin[a] = fminf(cmin[a], c[a]); cmax[a] = fmaxf(cmax[a], c[a]); }
+    }
+    for (int a = 0; a < 3; ++a)
+        for (int off = 16; off > 0; off >>= 1) {
+            cmin[a] = fminf(cmin[a], __shfl_xor_sync(FULLM, cmin[a], off));
+            cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(FULLM, cmax[a], off));
+        }
+    if (TEAM > 32) {
+        if (lane == 0) for (int a = 0; a < 3; ++a) { sb.red[a][wid] = cmin[a]; sb.red[3 + a][wid] = cmax[a]; }
+        __syncthreads();
+        for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < NW; ++k) { cmin[a] = fminf(cmin[a], sb.red[a][k]); cmax[a] = fmaxf(cmax[a], sb.red[3 + a][k]); }
+    }
+    float kbin[3];
+    for (int a = 0; a < 3; ++a) kbin[a] = cmax[a] > cmin[a] ? (float)SAH_BINS / (cmax[a] - cmin[a]) : 0.f;
+
+    // binning
+    for (int i = tid; i < 3 * SAH_BINS; i += TEAM) {
+        (&sb.cnt[0][0])[i] = 0u;
+        for (int k = 0; k < 3; ++k) { (&sb.lo[0][0][0])[3 * i + k] = 0xffffffffu; (&sb.hi[0][0][0])[3 * i + k] = 0u; }
+    }
+    team_sync();
+    for (uint32_t i = lo + tid; i < hi; i += TEAM) {
+        const uint32_t r = src[i];
+        const float4 l = plo[r], h = phi[r];
+        const float c[3] = {0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z)};
+        const uint32_t el[3] = {f2o(l.x), f2o(l.y), f2o(l.z)}, eh[3] = {f2o(h.x), f2o(h.y), f2o(h.z)};
+        for (int a = 0; a < 3; ++a) {
+            if (kbin[a] == 0.f) continue;
+            const int b = sah_bin(c[a], cmin[a], kbin[a]);
+            atomicAdd(&sb.cnt[a][b], 1u);
+            for (int k = 0; k < 3; ++k) { atomicMin(&sb.lo[a][b][k], el[k]); atomicMax(&sb.hi[a][b][k], eh[k]); }
+        }
+    }
+    team_sync();
+
+    // the 3 x (SAH_BINS - 1) candidate planes: cost = A(L) n_L + A(R) n_R
+    for (int cand = tid; cand < SAH_CAND; cand += TEAM) {
+        const int a = cand / (SAH_BINS - 1), k = cand % (SAH_BINS - 1);     // left = bins 0..k
+        float area[2] = {0.f, 0.f};
+        uint32_t cnt[2] = {0u, 0u};
+        for (int side = 0; side < 2; ++side) {
+            uint32_t blo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, bhi[3] = {0u, 0u, 0u};
+            for (int b = side ? k + 1 : 0; b <= (side ? SAH_BINS - 1 : k); ++b) {
+                if (!sb.cnt[a][b]) continue;
+                cnt[side] += sb.cnt[a][b];
+                for (int q = 0; q < 3; ++q) { blo[q] = min(blo[q], sb.lo[a][b][q]); bhi[q] = max(bhi[q], sb.hi[a][b][q]); }
+            }
+            if (cnt[side]) {
+                const float dx = o2f(bhi[0]) - o2f(blo[0]), dy = o2f(bhi[1]) - o2f(blo[1]), dz = o2f(bhi[2]) - o2f(blo[2]);
+                area[side] = dx * dy + dy * dz + dz * dx;
+            }
+        }
+        const bool valid = kbin[a] != 0.f && cnt[0] && cnt[1];
+        sb.cost[cand] = valid ? area[0] * (float)cnt[0] + area[1] * (float)cnt[1] : FLT_MAX;
+        sb.nl[cand] = cnt[0];
+    }
+    team_sync();
+    if (tid == 0) {
+        int best = -1;
+        float bc = FLT_MAX;
+        for (int c = 0; c < SAH_CAND; ++c) if (sb.cost[c] < bc) { bc = sb.cost[c]; best = c; }
+        sb.best = best;
+        sb.n_left = best >= 0 ? sb.nl[best] : count / 2u;
+    }
+    team_sync();
+    const int best = sb.best;
+    const uint32_t n_left = sb.n_left;
+
+    // stable partition of [lo, hi) from src into dst: left block, then right block
+    if (best < 0) {                       // all centroids coincide: split in the middle, order unchanged
+        for (uint32_t i = lo + tid; i < hi; i += TEAM) dst[i] = src[i];
+    } else {
+        const int a = best / (SAH_BINS - 1), k = best % (SAH_BINS - 1);
+        uint32_t base_l = lo, base_r = lo + n_left;
+        for (uint32_t i0 = lo; i0 < hi; i0 += TEAM) {
+            const uint32_t i = i0 + tid;
+            uint32_t r = 0;
+            bool left = false;
+            if (i < hi) {
+                r = src[i];
+                const float4 l = plo[r], h = phi[r];
+                const float c = a == 0 ? 0.5f * (l.x + h.x) : (a == 1 ? 0.5f * (l.y + h.y) : 0.5f * (l.z + h.z));
+                left = sah_bin(c, cmin[a], kbin[a]) <= k;
+            }
+            const unsigned ml = __ballot_sync(FULLM, i < hi && left), mr = __ballot_sync(FULLM, i < hi && !left);
+            const unsigned lt = (1u << lane) - 1u;
+            uint32_t off_l = 0, off_r = 0, tot_l = __popc(ml), tot_r = __popc(mr);
+            if (TEAM > 32) {
+                if (lane == 0) { sb.wl[wid] = tot_l; sb.wr[wid] = tot_r; }
+                __syncthreads();
+                tot_l = tot_r = 0;
+                for (int q = 0; q < NW; ++q) {
+                    if (q < (int)wid) { off_l += sb.wl[q]; off_r += sb.wr[q]; }
+                    tot_l += sb.wl[q]; tot_r += sb.wr[q];
+                }
+            }
+            if (i < hi) dst[left ? base_l + off_l + __popc(ml & lt) : base_r + off_r + __popc(mr & lt)] = r;
+            base_l += tot_l; base_r += tot_r;
+            if (TEAM > 32) __syncthreads();
+        }
+    }
+    __threadfence_block();
+    team_sync();
+
+    if (tid == 0) {
+        const uint32_t mid = lo + n_left;
+        int ids[2];
+        const uint32_t clo[2] = {lo, mid}, chi[2] = {mid, hi};
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t cc = chi[c] - clo[c];
+            if (cc == 1u) {
+                ids[c] = (int)(n - 1u + clo[c]);
+                leaf_vals[clo[c]] = dst[clo[c]];
+            } else {
+                ids[c] = (int)atomicAdd(&st->next_internal, 1u);
+                SahItem ni; ni.node = ids[c]; ni.lo = clo[c]; ni.hi = chi[c];
+                if (cc > SAH_BIG) next_big[atomicAdd(&st->n_next_big, 1u)] = ni;
+                else next_small[atomicAdd(&st->n_next_small, 1u)] = ni;
+            }
+            parent[ids[c]] = item.node;
+        }
+        children[item.node] = make_int2(ids[0], ids[1]);
+        range[item.node] = make_int2((int)lo, (int)hi - 1);
+        if (item.node == 0) parent[0] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(32 * SAH_WARPS)
+k_sah_level_small(const SahItem* __restrict__ items, uint32_t n_items, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                  const float4* __restrict__ plo, const float4* __restrict__ phi, uint32_t n, SahItem* __restrict__ next_small,
+                  SahItem* __restrict__ next_big, SahState* st, int2* __restrict__ children, int2* __restrict__ range,
+                  int* __restrict__ parent, uint32_t* __restrict__ leaf_vals) {
+    __shared__ SahBins sb[SAH_WARPS];
+    const uint32_t it = blockIdx.x * SAH_WARPS + (threadIdx.x >> 5);
+    if (it >= n_items) return;
+    sah_split_node<32>(items[it], threadIdx.x & 31u, sb[threadIdx.x >> 5], src, dst, plo, phi, n, next_small, next_big, st, children,
+                       range, parent, leaf_vals);
+}
+__global__ void __launch_bounds__(SAH_BIG_TEAM)
+k_sah_level_big(const SahItem* __restrict__ items, uint32_t n_items, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                const float4* __restrict__ plo, const float4* __restrict__ phi, uint32_t n, SahItem* __restrict__ next_small,
+                SahItem* __restrict__ next_big, SahState* st, int2* __restrict__ children, int2* __restrict__ range,
+                int* __restrict__ parent, uint32_t* __restrict__ leaf_vals) {
+    __shared__ SahBins sb;
+    if (blockIdx.x >= n_items) return;
+    sah_split_node<SAH_BIG_TEAM>(items[blockIdx.x], threadIdx.x, sb, src, dst, plo, phi, n, next_small, next_big, st, children, range,
+                                 parent, leaf_vals);
 }
 
 // Bottom-up refit.  blo/bhi are indexed by Karras node id (internal 0..n-2, leaf n-1+k).
@@ -733,8 +936,8 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     struct BuildEnv { int builder, ploc_r, sah_leaves, split_div; };
     static const BuildEnv benv = [] {
         BuildEnv e;
-        const char* b = getenv("RTB_BUILDER");        // "karras" = plain radix tree, default PLOC
-        e.builder = (b && b[0] == 'k') ? 0 : 1;
+        const char* b = getenv("RTB_BUILDER");        // "karras" = plain radix tree, "ploc" = PLOC, default binned SAH top-down
+        e.builder = (b && b[0] == 'k') ? 0 : ((b && b[0] == 'p') ? 1 : 2);
         const char* r = getenv("RTB_PLOC_R");
         e.ploc_r = r ? std::min(PLOC_R_MAX, std::max(1, atoi(r))) : 16;
         const char* l = getenv("RTB_SAH_LEAVES");
@@ -825,7 +1028,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     // PLOC scratch
     DevBuf<PlocState> pstate;
     DevBuf<float4> qlo, qhi;
-    DevBuf<uint32_t> cl_a, cl_b, nn, psize, vals_dfs;
+    DevBuf<uint32_t> cl_a, cl_b, nn, psize, vals_dfs, vals_dfs_sah;
     DevBuf<unsigned long long> pflags, ppos;
     DevBuf<int2> pchildren;
     DevBuf<int> pparent;
@@ -839,6 +1042,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     RTB_CUDA(kind.alloc(n_all));
     const int builder = benv.builder, ploc_r = benv.ploc_r, sah_leaves = benv.sah_leaves;
     const bool use_ploc = builder == 1 && n_int > 0 && !force_karras;
+    const bool use_sah = builder == 2 && n_int > 0 && !force_karras;
     if (use_ploc) {
         RTB_CUDA(pstate.alloc(2)); RTB_CUDA(qlo.alloc(n_all)); RTB_CUDA(qhi.alloc(n_all));
         RTB_CUDA(cl_a.alloc(n)); RTB_CUDA(cl_b.alloc(n)); RTB_CUDA(nn.alloc(n)); RTB_CUDA(psize.alloc(n_all));
@@ -896,6 +1100,38 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         k_ploc_finish<<<cdiv(n_int, B), B, 0, stream>>>(n, pchildren.p, pparent.p, psize.p, vals_sorted.p, children.p,
                                                         range.p, parent.p, vals_dfs.p); ++launches;
         leaf_vals = vals_dfs.p;
+    } else if (use_sah) {
+        RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
+        DevBuf<SahItem> ws[2], wbig[2];
+        DevBuf<SahState> sst;
+        DevBuf<uint32_t> ib;
+        for (int k = 0; k < 2; ++k) { RTB_CUDA(ws[k].alloc(n)); RTB_CUDA(wbig[k].alloc(n / SAH_BIG + 2)); }
+        RTB_CUDA(sst.alloc(1)); RTB_CUDA(ib.alloc(n)); RTB_CUDA(vals_dfs_sah.alloc(n));
+        // level L reads the index buffer idx[L & 1] and writes idx[(L + 1) & 1]; the Morton order is the starting order
+        uint32_t* idx[2] = {vals_sorted.p, ib.p};
+        SahItem root; root.node = 0; root.lo = 0; root.hi = n;
+        SahState hs; hs.n_next_small = hs.n_next_big = 0; hs.next_internal = 1; hs.pad = 0;
+        uint32_t n_small = n > SAH_BIG ? 0u : 1u, n_big = n > SAH_BIG ? 1u : 0u;
+        RTB_CUDA(cudaMemcpyAsync(n_big ? wbig[0].p : ws[0].p, &root, sizeof root, cudaMemcpyHostToDevice, stream));
+        RTB_CUDA(cudaMemcpyAsync(sst.p, &hs, sizeof hs, cudaMemcpyHostToDevice, stream));
+        for (int level = 0; n_small + n_big > 0; ++level) {
+            if (level > 2 * RTB_STACK) { rtb_set_error("SAH build does not terminate"); return RTB_ERR_CUDA; }
+            const int c = level & 1, x = c ^ 1;
+            if (n_big) {
+                k_sah_level_big<<<n_big, SAH_BIG_TEAM, 0, stream>>>(wbig[c].p, n_big, idx[c], idx[x], plo.p, phi.p, n, ws[x].p, wbig[x].p,
+                                                                    sst.p, children.p, range.p, parent.p, vals_dfs_sah.p); ++launches;
+            }
+            if (n_small) {
+                k_sah_level_small<<<cdiv(n_small, SAH_WARPS), 32 * SAH_WARPS, 0, stream>>>(ws[c].p, n_small, idx[c], idx[x], plo.p, phi.p, n,
+                                                                                          ws[x].p, wbig[x].p, sst.p, children.p, range.p,
+                                                                                          parent.p, vals_dfs_sah.p); ++launches;
+            }
+            RTB_CUDA(cudaMemcpyAsync(&hs, sst.p, sizeof hs, cudaMemcpyDeviceToHost, stream));
+            RTB_CUDA(cudaStreamSynchronize(stream));
+            n_small = hs.n_next_small; n_big = hs.n_next_big;
+            RTB_CUDA(cudaMemsetAsync(sst.p, 0, 2 * sizeof(uint32_t), stream));      // the two list counters, not next_internal
+        }
+        leaf_vals = vals_dfs_sah.p;
     } else if (n_int > 0) {
         RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
         k_hierarchy<<<cdiv(n_int, B), B, 0, stream>>>(keys_sorted.p, (int)n, children.p, range.p, parent.p); ++launches;
