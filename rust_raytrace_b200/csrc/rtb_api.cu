@@ -315,6 +315,16 @@ int rtb_init(int n_gpus, const int* device_ids) {
                 if (pe != cudaSuccess) cudaGetLastError();   // already enabled is fine
             }
         }
+    // scene-build scratch is stream-ordered (cudaMallocAsync): keep freed blocks in the pool instead of returning them
+    for (int d : devs) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+            uint64_t keep_all = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+        } else {
+            cudaGetLastError();
+        }
+    }
     RTB_CUDA(cudaSetDevice(devs[0]));
     g_devices = devs;
     return RTB_OK;
@@ -446,18 +456,18 @@ int scene_create_common(const TriSource& src, const float root_orig[3], float ro
         RtbTriangle* d_tris = nullptr;
         uint32_t* d_keep = nullptr;
         uint32_t n_prims = 0;
-        if ((e = cudaMalloc(&d_tris, sizeof(RtbTriangle) * (n ? n : 1))) != cudaSuccess)
-            return bail(rtb_cuda_fail(e, "cudaMalloc(tris)", __FILE__, __LINE__));
+        if ((e = cudaMallocAsync(&d_tris, sizeof(RtbTriangle) * (n ? n : 1), g.stream)) != cudaSuccess)
+            return bail(rtb_cuda_fail(e, "cudaMallocAsync(tris)", __FILE__, __LINE__));
         rc = produce_triangles(src, d_tris, g.stream);
         if (rc == RTB_OK) rc = rtb_launch_cull(d_tris, n, root_orig, root_len2, g.stream, &d_keep, &n_prims);
-        if (rc != RTB_OK) { cudaFree(d_tris); cudaFree(d_keep); return bail(rc); }
+        if (rc != RTB_OK) { cudaFreeAsync(d_tris, g.stream); cudaFreeAsync(d_keep, g.stream); return bail(rc); }
         const double t1 = now_ms();
         if (gi == 0) s->info.n_prims = n_prims;
 
         BuildResult br;
         rc = rtb_build_lbvh(d_tris, d_keep, n_prims, g.stream, &br);
-        cudaFree(d_tris);
-        cudaFree(d_keep);
+        cudaFreeAsync(d_tris, g.stream);
+        cudaFreeAsync(d_keep, g.stream);
         g.d_nodes = br.d_nodes; g.d_tri = br.d_tri; g.d_shade = br.d_shade; g.d_prim_order = br.d_prim_order;
         g.n_nodes = br.n_nodes;
         g.height = br.tree_height;

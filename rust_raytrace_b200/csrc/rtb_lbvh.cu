@@ -885,11 +885,15 @@ __global__ void k_emit_tris(const RtbTriangle* __restrict__ tris, const uint32_t
     prim_order[k] = orig;
 }
 
+// Build scratch comes from the device's stream-ordered pool (release threshold raised in rtb_init): with plain
+// cudaMalloc / cudaFree a 1 M-triangle build took 30 ms most of the time and 285 ms whenever the driver decided to
+// give memory back to the system and fetch it again.
+thread_local cudaStream_t t_alloc_stream = nullptr;
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, t_alloc_stream); }
+    cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), t_alloc_stream); }
 };
 
 inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -920,6 +924,7 @@ int rtb_build_lbvh(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n
 static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_t n, cudaStream_t stream,
                       bool force_karras, BuildResult* out) {
     *out = BuildResult();
+    t_alloc_stream = stream;
     // device time of the build = the bounds/split phase (s0..s1) + everything after the allocations (e0..e1)
     cudaEvent_t e0, e1, s0, s1, s2, s3;
     RTB_CUDA(cudaEventCreate(&e0));
@@ -1043,6 +1048,14 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     const int builder = benv.builder, ploc_r = benv.ploc_r, sah_leaves = benv.sah_leaves;
     const bool use_ploc = builder == 1 && n_int > 0 && !force_karras;
     const bool use_sah = builder == 2 && n_int > 0 && !force_karras;
+    // binned-SAH scratch: per-level work lists (small / big nodes), the second index buffer, the leaf order
+    DevBuf<SahItem> ws[2], wbig[2];
+    DevBuf<SahState> sst;
+    DevBuf<uint32_t> ib;
+    if (use_sah) {
+        for (int k = 0; k < 2; ++k) { RTB_CUDA(ws[k].alloc(n)); RTB_CUDA(wbig[k].alloc(n / SAH_BIG + 2)); }
+        RTB_CUDA(sst.alloc(1)); RTB_CUDA(ib.alloc(n)); RTB_CUDA(vals_dfs_sah.alloc(n));
+    }
     if (use_ploc) {
         RTB_CUDA(pstate.alloc(2)); RTB_CUDA(qlo.alloc(n_all)); RTB_CUDA(qhi.alloc(n_all));
         RTB_CUDA(cl_a.alloc(n)); RTB_CUDA(cl_b.alloc(n)); RTB_CUDA(nn.alloc(n)); RTB_CUDA(psize.alloc(n_all));
@@ -1102,11 +1115,6 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         leaf_vals = vals_dfs.p;
     } else if (use_sah) {
         RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
-        DevBuf<SahItem> ws[2], wbig[2];
-        DevBuf<SahState> sst;
-        DevBuf<uint32_t> ib;
-        for (int k = 0; k < 2; ++k) { RTB_CUDA(ws[k].alloc(n)); RTB_CUDA(wbig[k].alloc(n / SAH_BIG + 2)); }
-        RTB_CUDA(sst.alloc(1)); RTB_CUDA(ib.alloc(n)); RTB_CUDA(vals_dfs_sah.alloc(n));
         // level L reads the index buffer idx[L & 1] and writes idx[(L + 1) & 1]; the Morton order is the starting order
         uint32_t* idx[2] = {vals_sorted.p, ib.p};
         SahItem root; root.node = 0; root.lo = 0; root.hi = n;
@@ -1200,6 +1208,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
 // Self-test of the builder's sort and scan against the host (std::stable_sort / a running sum): n random pairs with
 // `key_bits` significant key bits (few bits = many equal keys = the stability check).  RTB_OK or RTB_ERR_INVALID.
 int rtb_sort_selftest(uint32_t n, int key_bits, uint64_t seed) {
+    t_alloc_stream = nullptr;            // scratch on the default stream (a previous build's stream may be gone)
     std::vector<unsigned long long> keys(n);
     std::vector<uint32_t> vals(n);
     uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;

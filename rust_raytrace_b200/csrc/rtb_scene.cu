@@ -226,16 +226,17 @@ int rtb_launch_assemble(const float* d_verts, uint32_t nverts, const uint32_t* d
 }
 
 // Root-cube cull + ordered compaction: *d_keep_out (cudaMalloc'ed here, caller frees) holds the indices of the
-// *n_keep triangles that enter the tree, ascending.  Synchronises the stream.
+// *n_keep triangles that enter the tree, ascending (stream-ordered allocation: free with cudaFreeAsync / cudaFree).
+// Synchronises the stream.
 int rtb_launch_cull(const RtbTriangle* d_tris, uint32_t n, const float root_orig[3], float root_len2,
                     cudaStream_t stream, uint32_t** d_keep_out, uint32_t* n_keep) {
     *d_keep_out = nullptr; *n_keep = 0;
     uint32_t *flags = nullptr, *pos = nullptr, *keep = nullptr;
     uint8_t* tmp = nullptr;
-    auto cleanup = [&] { cudaFree(flags); cudaFree(pos); cudaFree(tmp); };
-    cudaError_t e = cudaMalloc(&flags, sizeof(uint32_t) * ((size_t)n + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&pos, sizeof(uint32_t) * ((size_t)n + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&tmp, rtbsort::scan_tmp_bytes<uint32_t>(n + 1));
+    auto cleanup = [&] { cudaFreeAsync(flags, stream); cudaFreeAsync(pos, stream); cudaFreeAsync(tmp, stream); };
+    cudaError_t e = cudaMallocAsync(&flags, sizeof(uint32_t) * ((size_t)n + 1), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&pos, sizeof(uint32_t) * ((size_t)n + 1), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&tmp, rtbsort::scan_tmp_bytes<uint32_t>(n + 1), stream);
     if (e != cudaSuccess) { cleanup(); RTB_CUDA(e); }
     const float3 root = root_orig ? make_float3(root_orig[0], root_orig[1], root_orig[2]) : make_float3(0.f, 0.f, 0.f);
     k_cull_flags<<<(n + 1 + 127) / 128, 128, 0, stream>>>(d_tris, n, root, root_orig ? root_len2 : 0.f, flags);
@@ -243,14 +244,14 @@ int rtb_launch_cull(const RtbTriangle* d_tris, uint32_t n, const float root_orig
     uint32_t total = 0;
     e = cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e == cudaSuccess) e = cudaMalloc(&keep, sizeof(uint32_t) * (total ? total : 1));
+    if (e == cudaSuccess) e = cudaMallocAsync(&keep, sizeof(uint32_t) * (total ? total : 1), stream);
     if (e == cudaSuccess) {
         k_compact_keep<<<(n + 127) / 128 + 1, 128, 0, stream>>>(flags, pos, n, keep);
         e = cudaStreamSynchronize(stream);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     cleanup();
-    if (e != cudaSuccess) { cudaFree(keep); RTB_CUDA(e); }
+    if (e != cudaSuccess) { cudaFreeAsync(keep, stream); RTB_CUDA(e); }
     *d_keep_out = keep;
     *n_keep = total;
     return RTB_OK;
