@@ -334,6 +334,11 @@ int rtb_device_count(void) { return g_devices.empty() ? RTB_ERR_INVALID : (int)g
 
 void rtb_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    for (int d : g_devices) {            // hand the cached scene-build scratch back to the system
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        else cudaGetLastError();
+    }
     g_devices.clear();
     std::lock_guard<std::mutex> lr(g_render_mu);
     g_workers.clear();

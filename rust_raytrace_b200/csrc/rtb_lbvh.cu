@@ -734,7 +734,9 @@ __device__ __forceinline__ bool collapses(int c, int n, const int2* __restrict__
     const int sl = ch.x >= n - 1 ? 1 : range[ch.x].y - range[ch.x].x + 1;
     const int sr = ch.y >= n - 1 ? 1 : range[ch.y].y - range[ch.y].x + 1;
     const float a = box_area(blo[c], bhi[c]);
-    const float split = a + box_area(blo[ch.x], bhi[ch.x]) * (float)sl + box_area(blo[ch.y], bhi[ch.y]) * (float)sr;
+    // sah = cost of one more box test in percent of an exact triangle test (RTB_SAH_LEAVES; 1 means 100)
+    const float c_node = sah == 1 ? 1.0f : 0.01f * (float)sah;
+    const float split = a * c_node + box_area(blo[ch.x], bhi[ch.x]) * (float)sl + box_area(blo[ch.y], bhi[ch.y]) * (float)sr;
     return !(split < a * (float)size);
 }
 
