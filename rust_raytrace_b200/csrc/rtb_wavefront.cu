@@ -43,7 +43,8 @@ constexpr uint32_t WF_SENTINEL = 0x7fffffffu;   // bottom of a whole-in-shared-m
 // Tunables (env RTB_WF_DESCEND / RTB_WF_REFILL override for experiments).  Measured on B200, 4K teapot frame, current
 // pipeline with exact work fetch: (descend, refill) = (4,16) 2.82 ms, (4,20) 2.79, (4,24) 2.80, (4,28) 2.86,
 // (3,20) 2.79, (6,20) 2.87, (8,20) 2.90.
-constexpr uint32_t WF_DESCEND_MAX = 4;  // BVH4 node visits per lane per round before leaves are processed
+constexpr uint32_t WF_DESCEND_MAX = 3;  // BVH4 node visits per lane per round before leaves are processed (binned-SAH tree: 4 -> 3
+                                        // = 2.133 -> 2.102 ms on the 4K teapot frame, 1.120 -> 1.091 ms on the 1 M field)
 constexpr uint32_t WF_REFILL_MIN = 20;  // bounce kernel: service (shade / refill) lanes once at least this many wait
 constexpr uint32_t WF_REFILL_MIN_PRIMARY = 24;   // primary kernel: refill once at least this many lanes are done
 struct WfTune { uint32_t descend_max, refill_min; int smem_depth; uint32_t pool_node_min; };
