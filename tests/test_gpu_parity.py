@@ -526,3 +526,22 @@ def test_circles_2k_full_size(R, O):
     assert_bit_exact(got, _oracle_ext(O, s, O.ACCEL_BVH).render(ov, seed=7), "circles 2K")
     assert (got[1] >= len(s.tris)).mean() > 0.05          # spheres cover a good part of the frame
     s.release()
+
+
+def test_all_three_bvh_builders_give_the_same_frame(R, tmp_path):
+    """Size-independent property: the closest hit does not depend on the accelerator.  The driver binary is run once per
+    topology builder (binned SAH = default, PLOC, Karras radix tree; the knob is read once per process) and once without
+    reference splitting; every PNG must hold the same bytes and every run must count the same rays."""
+    import os
+    import subprocess
+    from rust_raytrace_b200 import _lib
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "raytrace_b200")
+    outs = []
+    for k, env in enumerate(({}, {"RTB_BUILDER": "ploc"}, {"RTB_BUILDER": "karras"}, {"RTB_SPLIT_DIV": "0"})):
+        out = str(tmp_path / f"b{k}.png")
+        r = subprocess.run([exe, "--mesh", R.raytrace.TEAPOT_MESH, "--size", "800x450", "--out", out, "--seed", "5"],
+                           capture_output=True, text=True, env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr
+        rays = [ln for ln in r.stdout.splitlines() if ln.startswith("Rays:")]
+        outs.append((open(out, "rb").read(), rays))
+    assert all(o == outs[0] for o in outs[1:])
