@@ -488,6 +488,7 @@ constexpr int SAH_BINS = 16;
 constexpr int SAH_CAND = 3 * (SAH_BINS - 1);
 constexpr int SAH_BIG_TEAM = 512;        // threads per node for nodes of more than SAH_BIG references (one CTA each)
 constexpr uint32_t SAH_BIG = 2048;
+constexpr uint32_t SAH_SAMPLES = 16384;  // big nodes of >= 2 x this many references bin a sample of about this size
 constexpr int SAH_WARPS = 4;             // small nodes: one warp each, this many per CTA
 struct SahItem { int node; uint32_t lo, hi; };     // references [lo, hi) of the level's input index buffer
 struct SahState { uint32_t n_next_small, n_next_big, next_internal, pad; };
@@ -517,10 +518,14 @@ __device__ void sah_split_node(const SahItem item, unsigned tid, SahBins& sb, co
     constexpr int NW = TEAM / 32;
     auto team_sync = [&]() { if (TEAM == 32) __syncwarp(); else __syncthreads(); };
     const uint32_t lo = item.lo, hi = item.hi, count = hi - lo;
+    // Very big nodes choose their plane from a sample (every `stride`-th reference, >= SAH_SAMPLES of them): the two
+    // binning passes then cost next to nothing and the node is read once, by the partition.  The sampled centroid
+    // bounds need not contain every centroid: sah_bin clamps, and the partition uses the same function.
+    const uint32_t stride = (TEAM > 32 && count >= 2u * SAH_SAMPLES) ? count / SAH_SAMPLES : 1u;
 
     // centroid bounds
     float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (uint32_t i = lo + tid; i < hi; i += TEAM) {
+    for (uint32_t i = lo + tid * stride; i < hi; i += TEAM * stride) {
         const uint32_t r = src[i];
         const float4 l = plo[r], h = phi[r];
         const float c[3] = {0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z)};
@@ -546,7 +551,7 @@ __device__ void sah_split_node(const SahItem item, unsigned tid, SahBins& sb, co
         for (int k = 0; k < 3; ++k) { (&sb.lo[0][0][0])[3 * i + k] = 0xffffffffu; (&sb.hi[0][0][0])[3 * i + k] = 0u; }
     }
     team_sync();
-    for (uint32_t i = lo + tid; i < hi; i += TEAM) {
+    for (uint32_t i = lo + tid * stride; i < hi; i += TEAM * stride) {
         const uint32_t r = src[i];
         const float4 l = plo[r], h = phi[r];
         const float c[3] = {0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z)};
@@ -591,14 +596,16 @@ __device__ void sah_split_node(const SahItem item, unsigned tid, SahBins& sb, co
     }
     team_sync();
     const int best = sb.best;
-    const uint32_t n_left = sb.n_left;
+    uint32_t n_left = sb.n_left;
 
     // stable partition of [lo, hi) from src into dst: left block, then right block
     if (best < 0) {                       // all centroids coincide: split in the middle, order unchanged
         for (uint32_t i = lo + tid; i < hi; i += TEAM) dst[i] = src[i];
     } else {
         const int a = best / (SAH_BINS - 1), k = best % (SAH_BINS - 1);
-        uint32_t base_l = lo, base_r = lo + n_left;
+        // a warp knows n_left from the bin counts and writes two forward blocks (stable); a CTA (whose counts may come
+        // from a sample) fills the right block from the back and counts n_left as it goes
+        uint32_t base_l = lo, base_r = TEAM > 32 ? 0u : lo + n_left;
         for (uint32_t i0 = lo; i0 < hi; i0 += TEAM) {
             const uint32_t i = i0 + tid;
             uint32_t r = 0;
@@ -621,10 +628,14 @@ __device__ void sah_split_node(const SahItem item, unsigned tid, SahBins& sb, co
                     tot_l += sb.wl[q]; tot_r += sb.wr[q];
                 }
             }
-            if (i < hi) dst[left ? base_l + off_l + __popc(ml & lt) : base_r + off_r + __popc(mr & lt)] = r;
+            if (i < hi) {
+                const uint32_t rr = base_r + off_r + __popc(mr & lt);
+                dst[left ? base_l + off_l + __popc(ml & lt) : (TEAM > 32 ? hi - 1u - rr : rr)] = r;
+            }
             base_l += tot_l; base_r += tot_r;
             if (TEAM > 32) __syncthreads();
         }
+        if (TEAM > 32) n_left = base_l - lo;
     }
     __threadfence_block();
     team_sync();
