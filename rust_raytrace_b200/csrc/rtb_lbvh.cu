@@ -1136,7 +1136,12 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaMemcpyAsync(n_big ? wbig[0].p : ws[0].p, &root, sizeof root, cudaMemcpyHostToDevice, stream));
         RTB_CUDA(cudaMemcpyAsync(sst.p, &hs, sizeof hs, cudaMemcpyHostToDevice, stream));
         for (int level = 0; n_small + n_big > 0; ++level) {
-            if (level > 2 * RTB_STACK) { rtb_set_error("SAH build does not terminate"); return RTB_ERR_CUDA; }
+            if (level + 2 > RTB_STACK) {      // a chain deeper than the traversal stack: let the caller fall back to the radix tree
+                RTB_CUDA(cudaStreamSynchronize(stream));
+                out->tree_height = RTB_STACK;
+                rtb_set_error("SAH tree deeper than the traversal stack");
+                return RTB_ERR_INVALID;
+            }
             const int c = level & 1, x = c ^ 1;
             if (n_big) {
                 k_sah_level_big<<<n_big, SAH_BIG_TEAM, 0, stream>>>(wbig[c].p, n_big, idx[c], idx[x], plo.p, phi.p, n, ws[x].p, wbig[x].p,

@@ -545,3 +545,4 @@ def test_all_three_bvh_builders_give_the_same_frame(R, tmp_path):
         rays = [ln for ln in r.stdout.splitlines() if ln.startswith("Rays:")]
         outs.append((open(out, "rb").read(), rays))
     assert all(o == outs[0] for o in outs[1:])
+
