@@ -825,11 +825,77 @@ __global__ void k_flag4(int n_internal, const uint8_t* __restrict__ kind, const 
     if (kept) atomicMax(&s->depth4, depth >> 1);
 }
 
+
+// ---- 4-wide collapse by dynamic programming (default; RTB_COLLAPSE=even selects the rule above) -----------------------
+// Which descendants of a BVH2 node v become the (up to four) entries of its BVH4 node is chosen to minimise
+//   cost4(v) = A(v) + min over cuts C of v's subtree, |C| <= 4, of  sum_{c in C} cost4(c),   cost4(leaf) = 1.2 A(leaf) |leaf|
+// (one node visit per unit of area hit, 1.2 per exact triangle test).  The eight cuts with at most four members are
+// enumerated bottom-up (k_cost4, the arrival-counter walk of k_refit); the BVH4 roots are then marked top-down, one pass
+// per BVH4 level (k_mark4).  CPU experiment (tools/experiments/bvh_quality.cpp): 4.7 % fewer node visits per bounce ray
+// and 21 % fewer BVH4 nodes than "grandchildren at even depth" on the binned-SAH tree of the teapot scene.
+__device__ __forceinline__ float cost_of(const float* cost4, int c) { return __ldcg(cost4 + c); }
+
+__global__ void k_cost4(int n, const int2* __restrict__ children, const int2* __restrict__ range,
+                        const int* __restrict__ parent, const float4* __restrict__ blo, const float4* __restrict__ bhi,
+                        const uint8_t* __restrict__ kind, float* cost4, int4* __restrict__ cut, uint32_t* arrive) {
+    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c0 >= 2 * n - 1 || kind[c0] != KIND_LEAF) return;
+    const int cnt = c0 >= n - 1 ? 1 : range[c0].y - range[c0].x + 1;
+    cost4[c0] = 1.2f * box_area(blo[c0], bhi[c0]) * (float)cnt;
+    __threadfence();
+    auto internal = [&](int x) { return kind[x] == KIND_INTERNAL; };
+    for (int v = parent[c0]; v >= 0; v = parent[v]) {
+        if (atomicAdd(&arrive[v], 1u) == 0u) break;          // the sibling subtree is not finished yet
+        __threadfence();
+        const int2 ch = children[v];
+        const int l = ch.x, r = ch.y;
+        float best = cost_of(cost4, l) + cost_of(cost4, r);
+        int4 bc = make_int4(l, r, -1, -1);
+        auto consider = [&](int a, int b, int c, int d) {
+            const float s = cost_of(cost4, a) + cost_of(cost4, b) + cost_of(cost4, c) + (d >= 0 ? cost_of(cost4, d) : 0.f);
+            if (s < best) { best = s; bc = make_int4(a, b, c, d); }
+        };
+        int2 cl = make_int2(-1, -1), cr = make_int2(-1, -1);
+        if (internal(l)) { cl = children[l]; consider(cl.x, cl.y, r, -1); }
+        if (internal(r)) { cr = children[r]; consider(l, cr.x, cr.y, -1); }
+        if (internal(l) && internal(r)) consider(cl.x, cl.y, cr.x, cr.y);
+        if (internal(l)) {
+            if (internal(cl.x)) { const int2 g = children[cl.x]; consider(g.x, g.y, cl.y, r); }
+            if (internal(cl.y)) { const int2 g = children[cl.y]; consider(cl.x, g.x, g.y, r); }
+        }
+        if (internal(r)) {
+            if (internal(cr.x)) { const int2 g = children[cr.x]; consider(l, g.x, g.y, cr.y); }
+            if (internal(cr.y)) { const int2 g = children[cr.y]; consider(l, cr.x, g.x, g.y); }
+        }
+        cut[v] = bc;
+        cost4[v] = box_area(blo[v], bhi[v]) + best;
+        __threadfence();
+    }
+}
+
+// lvl4[v] = BVH4 depth of v where v is a BVH4 root, -1 elsewhere.  Pass `level` marks the entries of the roots of that level.
+__global__ void k_mark4(int n_internal, int level, const uint8_t* __restrict__ kind, const int4* __restrict__ cut,
+                        int* lvl4, uint32_t* __restrict__ flags4, BuildScratch* s) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_internal || lvl4[v] != level || kind[v] != KIND_INTERNAL) return;
+    const int4 c = cut[v];
+    const int e[4] = {c.x, c.y, c.z, c.w};
+    for (int k = 0; k < 4; ++k)
+        if (e[k] >= 0 && e[k] < n_internal && kind[e[k]] == KIND_INTERNAL) { lvl4[e[k]] = level + 1; flags4[e[k]] = 1u; }
+    atomicMax(&s->depth4, (uint32_t)level + 1u);
+}
+__global__ void k_mark4_init(int n_internal, int* lvl4, uint32_t* flags4) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_internal) return;
+    lvl4[v] = v == 0 ? 0 : -1;
+    flags4[v] = v == 0 ? 1u : 0u;
+}
+
 __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                               const float4* __restrict__ blo, const float4* __restrict__ bhi,
                               const uint32_t* __restrict__ flags4, const uint32_t* __restrict__ idx4,
                               const uint8_t* __restrict__ kind, float4* __restrict__ nodes4,
-                              const BuildScratch* __restrict__ s) {
+                              const BuildScratch* __restrict__ s, const int4* __restrict__ cut) {
     const int n_internal = n - 1;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_internal > 0 ? n_internal : 1)) return;
@@ -840,7 +906,11 @@ __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const in
     int n_ent = 0;
     if (n_internal == 0) ent[n_ent++] = 0;                       // the single Karras leaf
     else if (leaf_final(i)) ent[n_ent++] = i;                    // tiny scene: the root itself is a leaf
-    else {
+    else if (cut) {                                              // entries chosen by k_cost4
+        const int4 c = cut[i];
+        const int e4[4] = {c.x, c.y, c.z, c.w};
+        for (int k = 0; k < 4; ++k) if (e4[k] >= 0) ent[n_ent++] = e4[k];
+    } else {
         const int2 ch = children[i];
         const int cs[2] = {ch.x, ch.y};
         for (int k = 0; k < 2; ++k) {
@@ -951,7 +1021,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     uint32_t launches = 0;
 
     // experiment knobs, read once (thread-safe function-local static)
-    struct BuildEnv { int builder, ploc_r, sah_leaves, split_div; };
+    struct BuildEnv { int builder, ploc_r, sah_leaves, split_div, collapse_dp; };
     static const BuildEnv benv = [] {
         BuildEnv e;
         const char* b = getenv("RTB_BUILDER");        // "karras" = plain radix tree, "ploc" = PLOC, default binned SAH top-down
@@ -960,6 +1030,8 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         e.ploc_r = r ? std::min(PLOC_R_MAX, std::max(1, atoi(r))) : 16;
         const char* l = getenv("RTB_SAH_LEAVES");
         e.sah_leaves = l ? atoi(l) : 1;
+        const char* c4 = getenv("RTB_COLLAPSE");       // "even" = grandchildren at even depth, default: dynamic programming
+        e.collapse_dp = (c4 && c4[0] == 'e') ? 0 : 1;
         const char* d = getenv("RTB_SPLIT_DIV");      // split references longer than scene extent / this; 0 = off
         e.split_div = d ? std::max(0, atoi(d)) : 16;
         return e;
@@ -1061,6 +1133,11 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     const int builder = benv.builder, ploc_r = benv.ploc_r, sah_leaves = benv.sah_leaves;
     const bool use_ploc = builder == 1 && n_int > 0 && !force_karras;
     const bool use_sah = builder == 2 && n_int > 0 && !force_karras;
+    const bool collapse_dp = benv.collapse_dp != 0;
+    DevBuf<float> cost4;
+    DevBuf<int4> cut4;
+    DevBuf<int> lvl4;
+    if (collapse_dp) { RTB_CUDA(cost4.alloc(n_all)); RTB_CUDA(cut4.alloc(n_int)); RTB_CUDA(lvl4.alloc(n_int)); }
     // binned-SAH scratch: per-level work lists (small / big nodes), the second index buffer, the leaf order
     DevBuf<SahItem> ws[2], wbig[2];
     DevBuf<SahState> sst;
@@ -1088,7 +1165,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
                                                         vals_sorted.p, n, 63, sort_tmp.p, stream, &in_b);
         if (!in_b) { std::swap(keys.p, keys_sorted.p); std::swap(vals.p, vals_sorted.p); }   // result -> *_sorted
     }
-    uint32_t total_split = 0;
+    uint32_t total_split = 0, tree_height_host = 0;
     const uint32_t* leaf_vals = vals_sorted.p;     // primitive of every leaf, in leaf order
     if (use_ploc) {
         RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
@@ -1175,6 +1252,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaMemsetAsync(flags.p + n_int, 0, sizeof(uint32_t), stream));
         launches += (uint32_t)rtbsort::exclusive_sum<uint32_t>(flags.p, slot.p, n_int + 1, sort_tmp.p, stream);
         RTB_CUDA(cudaMemcpyAsync(&total_split, slot.p + n_int, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        RTB_CUDA(cudaMemcpyAsync(&tree_height_host, &scratch.p->height, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
     }
     out->n_nodes = 2 + 2 * total_split;
@@ -1186,7 +1264,19 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     // 4-wide collapse of the same tree (used by the wavefront renderer)
     uint32_t total4 = 1;
     if (n_int > 0) {
-        k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, kind.p, parent.p, flags4.p, scratch.p); ++launches;
+        if (collapse_dp) {
+            RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
+            k_cost4<<<cdiv(n_all, B), B, 0, stream>>>((int)n, children.p, range.p, parent.p, blo.p, bhi.p, kind.p, cost4.p, cut4.p,
+                                                      arrive.p); ++launches;
+            k_mark4_init<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, lvl4.p, flags4.p); ++launches;
+            // one marking pass per possible BVH4 level: a BVH4 level spans at least one BVH2 level (height is on the host
+            // from the read-back after k_node_kind)
+            for (uint32_t level = 0; level < tree_height_host; ++level) {
+                k_mark4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, (int)level, kind.p, cut4.p, lvl4.p, flags4.p, scratch.p); ++launches;
+            }
+        } else {
+            k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, kind.p, parent.p, flags4.p, scratch.p); ++launches;
+        }
         RTB_CUDA(cudaMemsetAsync(flags4.p + n_int, 0, sizeof(uint32_t), stream));
         launches += (uint32_t)rtbsort::exclusive_sum<uint32_t>(flags4.p, idx4.p, n_int + 1, sort_tmp.p, stream);
         RTB_CUDA(cudaMemcpyAsync(&total4, idx4.p + n_int, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -1195,7 +1285,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     out->n_nodes4 = total4;
     RTB_CUDA(cudaMalloc(&out->d_nodes4, sizeof(float4) * 8 * (size_t)total4));
     k_emit_nodes4<<<cdiv(n_int > 0 ? n_int : 1, B), B, 0, stream>>>((int)n, children.p, range.p, blo.p, bhi.p, flags4.p,
-                                                                  idx4.p, kind.p, out->d_nodes4, scratch.p); ++launches;
+                                                                  idx4.p, kind.p, out->d_nodes4, scratch.p, collapse_dp ? cut4.p : nullptr); ++launches;
     RTB_CUDA(cudaEventRecord(e1, stream));
     BuildScratch h;
     RTB_CUDA(cudaMemcpyAsync(&h, scratch.p, sizeof h, cudaMemcpyDeviceToHost, stream));
