@@ -837,11 +837,11 @@ __device__ __forceinline__ float cost_of(const float* cost4, int c) { return __l
 
 __global__ void k_cost4(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                         const int* __restrict__ parent, const float4* __restrict__ blo, const float4* __restrict__ bhi,
-                        const uint8_t* __restrict__ kind, float* cost4, int4* __restrict__ cut, uint32_t* arrive) {
+                        const uint8_t* __restrict__ kind, float* cost4, int4* __restrict__ cut, uint32_t* arrive, float c_tri) {
     const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (c0 >= 2 * n - 1 || kind[c0] != KIND_LEAF) return;
     const int cnt = c0 >= n - 1 ? 1 : range[c0].y - range[c0].x + 1;
-    cost4[c0] = 1.2f * box_area(blo[c0], bhi[c0]) * (float)cnt;
+    cost4[c0] = c_tri * box_area(blo[c0], bhi[c0]) * (float)cnt;
     __threadfence();
     auto internal = [&](int x) { return kind[x] == KIND_INTERNAL; };
     for (int v = parent[c0]; v >= 0; v = parent[v]) {
@@ -1021,7 +1021,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     uint32_t launches = 0;
 
     // experiment knobs, read once (thread-safe function-local static)
-    struct BuildEnv { int builder, ploc_r, sah_leaves, split_div, collapse_dp; };
+    struct BuildEnv { int builder, ploc_r, sah_leaves, split_div, collapse_dp, collapse_ct; };
     static const BuildEnv benv = [] {
         BuildEnv e;
         const char* b = getenv("RTB_BUILDER");        // "karras" = plain radix tree, "ploc" = PLOC, default binned SAH top-down
@@ -1032,6 +1032,8 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         e.sah_leaves = l ? atoi(l) : 1;
         const char* c4 = getenv("RTB_COLLAPSE");       // "even" = grandchildren at even depth, default: dynamic programming
         e.collapse_dp = (c4 && c4[0] == 'e') ? 0 : 1;
+        const char* ct = getenv("RTB_COLLAPSE_CT");    // cost of an exact triangle test in percent of a node visit
+        e.collapse_ct = ct ? std::max(1, atoi(ct)) : 120;
         const char* d = getenv("RTB_SPLIT_DIV");      // split references longer than scene extent / this; 0 = off
         e.split_div = d ? std::max(0, atoi(d)) : 16;
         return e;
@@ -1267,7 +1269,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         if (collapse_dp) {
             RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
             k_cost4<<<cdiv(n_all, B), B, 0, stream>>>((int)n, children.p, range.p, parent.p, blo.p, bhi.p, kind.p, cost4.p, cut4.p,
-                                                      arrive.p); ++launches;
+                                                      arrive.p, 0.01f * (float)benv.collapse_ct); ++launches;
             k_mark4_init<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, lvl4.p, flags4.p); ++launches;
             // one marking pass per possible BVH4 level: a BVH4 level spans at least one BVH2 level (height is on the host
             // from the read-back after k_node_kind)
