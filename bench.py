@@ -56,7 +56,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_wf_bounce launch of the teapot4k frame at N=1, from the
 # `ncu --set full` capture summarised in profiles/ (see DESIGN.md "Roofline"); null for every other configuration.
-NCU_TRAFFIC_BOUNCE_TEAPOT4K = 369.1e6   # profiles/r1_v9_k_wf_bounce_raw.csv: 257.3 MB read + 111.8 MB written
+NCU_TRAFFIC_BOUNCE_TEAPOT4K = 371.7e6   # profiles/r1_v10_k_wf_bounce_raw.csv: 258.7 MB read + 113.0 MB written
 
 
 def measured_peaks():

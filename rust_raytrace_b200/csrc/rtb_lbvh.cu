@@ -880,9 +880,10 @@ __global__ void k_mark4(int n_internal, int level, const uint8_t* __restrict__ k
     if (v >= n_internal || lvl4[v] != level || kind[v] != KIND_INTERNAL) return;
     const int4 c = cut[v];
     const int e[4] = {c.x, c.y, c.z, c.w};
+    bool any = false;
     for (int k = 0; k < 4; ++k)
-        if (e[k] >= 0 && e[k] < n_internal && kind[e[k]] == KIND_INTERNAL) { lvl4[e[k]] = level + 1; flags4[e[k]] = 1u; }
-    atomicMax(&s->depth4, (uint32_t)level + 1u);
+        if (e[k] >= 0 && e[k] < n_internal && kind[e[k]] == KIND_INTERNAL) { lvl4[e[k]] = level + 1; flags4[e[k]] = 1u; any = true; }
+    if (any) atomicMax(&s->depth4, (uint32_t)level + 1u);
 }
 __global__ void k_mark4_init(int n_internal, int* lvl4, uint32_t* flags4) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
