@@ -2,15 +2,18 @@
 // build_bounding_box raytrace.rs:790-845, with an accelerator that returns the same
 // closest hit; see DESIGN.md for the equivalence argument).
 //
-// Pipeline (all on one stream, no host round trip until the final info read-back):
+// Pipeline (all on one stream; host round trips only to read counts that size the next allocations / grids):
 //   k_prim_bounds   per-primitive AABB from `corners`, scene AABB by atomic min/max
+//   k_split_refs    reference splitting: long primitives enter as several clipped references (count, scan, emit)
 //   k_morton        63-bit Morton code of the AABB centre
-//   radix sort      (key = morton, value = primitive): 8 stable LSD passes of 8 bits, rtb_sort.cuh
-//   k_hierarchy     Karras 2012 radix-tree: children, parent, covered range per internal node
+//   radix sort      (key = morton, value = reference): 8 stable LSD passes of 8 bits, rtb_sort.cuh
+//   topology        k_sah_level_small/big (binned-SAH top-down, default) | k_ploc_* (PLOC) | k_hierarchy (Karras 2012
+//                   radix tree, also the fallback for over-deep trees): children, parent, covered range per node
 //   k_refit         bottom-up AABB union with one atomic arrival counter per internal node
-//   exclusive scan  over "this internal node stays internal" (rtb_sort.cuh)
-//   k_emit_nodes    collapse small subtrees into leaves, write 32-byte nodes with adjacent sibling pairs
-//   k_emit_tris     gather the 19 intersect floats + shading record of each primitive into leaf order
+//   k_node_kind     subtrees of <= RTB_LEAF_MAX references become leaves unless the SAH prefers the split
+//   k_emit_nodes    32-byte BVH2 nodes with adjacent sibling pairs (one-kernel renderers, rtb_scene_download_bvh)
+//   k_emit_tris     gather the 19 intersect floats + shading record of each reference into leaf order
+//   k_cost4/k_mark4/k_emit_nodes4   4-wide collapse chosen by dynamic programming, 128-byte BVH4 nodes (wavefront renderer)
 
 #include <algorithm>
 #include <cfloat>
