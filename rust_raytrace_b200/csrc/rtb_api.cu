@@ -162,7 +162,7 @@ SceneDev scene_dev(const GpuScene& g, uint32_t n_prims) {
     s.nodes = g.d_nodes; s.tri = g.d_tri; s.shade = g.d_shade; s.n_prims = n_prims; s.n_nodes = g.n_nodes;
     s.height = g.height;
     s.nodes4 = g.d_nodes4;
-    s.stack4 = 3u * (g.depth4 + 1u) + 2u;
+    s.stack4 = g.stack4_need ? g.stack4_need + 1u : 3u * (g.depth4 + 1u) + 2u;    // exact bound from the builder, else 3 per level
     return s;
 }
 
@@ -476,7 +476,7 @@ int scene_create_common(const TriSource& src, const float root_orig[3], float ro
         g.d_nodes = br.d_nodes; g.d_tri = br.d_tri; g.d_shade = br.d_shade; g.d_prim_order = br.d_prim_order;
         g.n_nodes = br.n_nodes;
         g.height = br.tree_height;
-        g.d_nodes4 = br.d_nodes4; g.n_nodes4 = br.n_nodes4; g.depth4 = br.depth4;
+        g.d_nodes4 = br.d_nodes4; g.n_nodes4 = br.n_nodes4; g.depth4 = br.depth4; g.stack4_need = br.stack4_need;
         g.has_spheres = src.n_spheres > 0;
         if (rc != RTB_OK) return bail(rc);
         if (gi == 0) {

@@ -122,7 +122,7 @@ struct GpuScene {
     uint32_t n_nodes = 0;
     uint32_t height = 0;
     float4* d_nodes4 = nullptr;
-    uint32_t n_nodes4 = 0, depth4 = 0;
+    uint32_t n_nodes4 = 0, depth4 = 0, stack4_need = 0;
     GpuLane lanes[RTB_MAX_LANES];
     cudaEvent_t fork_ev = nullptr;
     // scenes with analytic spheres or a light are rendered by the extension renderer (rtb_ext.cu)
@@ -154,7 +154,7 @@ struct BuildResult {
     uint32_t n_nodes = 0, n_leaves = 0, max_leaf = 0, tree_height = 0;
     uint32_t n_refs = 0;             // primitive references in the tree (>= n_prims: long primitives are split)
     float4* d_nodes4 = nullptr;      // 4-wide collapse, 8 x float4 per node
-    uint32_t n_nodes4 = 0, depth4 = 0;
+    uint32_t n_nodes4 = 0, depth4 = 0, stack4_need = 0;   // stack4_need: exact BVH4 stack bound (0 = use 3 per level)
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     float ms_build = 0.f;
     uint32_t launches = 0;

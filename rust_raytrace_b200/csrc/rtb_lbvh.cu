@@ -45,12 +45,13 @@ struct BuildScratch {
     uint32_t max_leaf;
     uint32_t n_leaves;
     uint32_t depth4;        // depth of the deepest 4-wide node (root = 0)
+    uint32_t stack_need;    // exact worst-case BVH4 traversal stack: max over root-to-node paths of sum (entries - 1); 0 = not computed
 };
 
 __global__ void k_init_scratch(BuildScratch* s) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         for (int k = 0; k < 3; ++k) { s->scene_lo[k] = 0xffffffffu; s->scene_hi[k] = 0u; }
-        s->max_abs = 0u; s->height = 0u; s->max_leaf = 0u; s->n_leaves = 0u; s->depth4 = 0u;
+        s->max_abs = 0u; s->height = 0u; s->max_leaf = 0u; s->n_leaves = 0u; s->depth4 = 0u; s->stack_need = 0u;
     }
 }
 
@@ -877,21 +878,31 @@ __global__ void k_cost4(int n, const int2* __restrict__ children, const int2* __
 }
 
 // lvl4[v] = BVH4 depth of v where v is a BVH4 root, -1 elsewhere.  Pass `level` marks the entries of the roots of that level.
+// It also accumulates the exact stack bound: when the traversal stands at a BVH4 node, the stack holds at most the
+// other entries of every node on the path to it, so need(v) = need(parent4(v)) + entries(v) - 1 (3 per level would be the
+// crude bound; the shared-memory stack of the persistent kernels is sized from this).
 __global__ void k_mark4(int n_internal, int level, const uint8_t* __restrict__ kind, const int4* __restrict__ cut,
-                        int* lvl4, uint32_t* __restrict__ flags4, BuildScratch* s) {
+                        int* lvl4, int* sacc, uint32_t* __restrict__ flags4, BuildScratch* s) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_internal || lvl4[v] != level || kind[v] != KIND_INTERNAL) return;
     const int4 c = cut[v];
     const int e[4] = {c.x, c.y, c.z, c.w};
+    int n_ent = 0;
+    for (int k = 0; k < 4; ++k) n_ent += e[k] >= 0 ? 1 : 0;
+    const int need = sacc[v] + n_ent - 1;
+    atomicMax(&s->stack_need, (uint32_t)need);
     bool any = false;
     for (int k = 0; k < 4; ++k)
-        if (e[k] >= 0 && e[k] < n_internal && kind[e[k]] == KIND_INTERNAL) { lvl4[e[k]] = level + 1; flags4[e[k]] = 1u; any = true; }
+        if (e[k] >= 0 && e[k] < n_internal && kind[e[k]] == KIND_INTERNAL) {
+            lvl4[e[k]] = level + 1; sacc[e[k]] = need; flags4[e[k]] = 1u; any = true;
+        }
     if (any) atomicMax(&s->depth4, (uint32_t)level + 1u);
 }
-__global__ void k_mark4_init(int n_internal, int* lvl4, uint32_t* flags4) {
+__global__ void k_mark4_init(int n_internal, int* lvl4, int* sacc, uint32_t* flags4) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_internal) return;
     lvl4[v] = v == 0 ? 0 : -1;
+    sacc[v] = 0;
     flags4[v] = v == 0 ? 1u : 0u;
 }
 
@@ -1142,8 +1153,8 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     const bool collapse_dp = benv.collapse_dp != 0;
     DevBuf<float> cost4;
     DevBuf<int4> cut4;
-    DevBuf<int> lvl4;
-    if (collapse_dp) { RTB_CUDA(cost4.alloc(n_all)); RTB_CUDA(cut4.alloc(n_int)); RTB_CUDA(lvl4.alloc(n_int)); }
+    DevBuf<int> lvl4, sacc4;
+    if (collapse_dp) { RTB_CUDA(cost4.alloc(n_all)); RTB_CUDA(cut4.alloc(n_int)); RTB_CUDA(lvl4.alloc(n_int)); RTB_CUDA(sacc4.alloc(n_int)); }
     // binned-SAH scratch: per-level work lists (small / big nodes), the second index buffer, the leaf order
     DevBuf<SahItem> ws[2], wbig[2];
     DevBuf<SahState> sst;
@@ -1274,11 +1285,11 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
             RTB_CUDA(cudaMemsetAsync(arrive.p, 0, sizeof(uint32_t) * n_int, stream));
             k_cost4<<<cdiv(n_all, B), B, 0, stream>>>((int)n, children.p, range.p, parent.p, blo.p, bhi.p, kind.p, cost4.p, cut4.p,
                                                       arrive.p, 0.01f * (float)benv.collapse_ct); ++launches;
-            k_mark4_init<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, lvl4.p, flags4.p); ++launches;
+            k_mark4_init<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, lvl4.p, sacc4.p, flags4.p); ++launches;
             // one marking pass per possible BVH4 level: a BVH4 level spans at least one BVH2 level (height is on the host
             // from the read-back after k_node_kind)
             for (uint32_t level = 0; level < tree_height_host; ++level) {
-                k_mark4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, (int)level, kind.p, cut4.p, lvl4.p, flags4.p, scratch.p); ++launches;
+                k_mark4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, (int)level, kind.p, cut4.p, lvl4.p, sacc4.p, flags4.p, scratch.p); ++launches;
             }
         } else {
             k_flag4<<<cdiv(n_int, B), B, 0, stream>>>((int)n_int, kind.p, parent.p, flags4.p, scratch.p); ++launches;
@@ -1308,6 +1319,7 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     for (int k = 0; k < 3; ++k) { out->lo[k] = dec(h.scene_lo[k]); out->hi[k] = dec(h.scene_hi[k]); }
     out->tree_height = h.height;
     out->depth4 = h.depth4;
+    out->stack4_need = h.stack_need;
     out->max_leaf = h.max_leaf;
     out->n_leaves = h.n_leaves;
     out->launches = launches;
