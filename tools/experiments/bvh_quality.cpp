@@ -1,10 +1,13 @@
 // bvh_quality.cpp — CPU experiment (not product code): how many BVH4 node visits / triangle tests per ray do
-// different BVH2 topologies need on the benchmark scene?  Builders: Morton LBVH (what rtb_lbvh.cu builds),
-// PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) and a binned-SAH top-down build as the
-// quality yardstick.  All three are collapsed to leaves of <= 4 primitives and to BVH4 the way the GPU builder does
-// (grandchildren at even depth) and traversed like rtb_wavefront.cu (sorted children, t_best culling).
+// different BVH2 topologies and 4-wide collapses need on the benchmark scene?  Builders: Morton LBVH, PLOC (parallel
+// locally-ordered clustering, Meister & Bittner 2018) and a binned-SAH top-down build; optional reference splitting
+// (primitives longer than argv[3] are clipped into several references); collapse to BVH4 by "grandchildren at even
+// depth", greedily by area, or by dynamic programming over the cuts of <= 4 nodes; traversal like rtb_wavefront.cu
+// (sorted children, t_best culling).  Every tree change of round 1 was measured here before it was built on the GPU.
 //
-//   g++ -O2 -o /tmp/bq/bq tools/experiments/bvh_quality.cpp && /tmp/bq/bq /tmp/bq/corners.bin
+//   python tools/dump_corners.py /tmp/bq/corners.bin
+//   g++ -O2 -o /tmp/bq/bq tools/experiments/bvh_quality.cpp && /tmp/bq/bq /tmp/bq/corners.bin 6320 0.556
+//   (argv[2] = primitives below this index bounce like the Matte teapot, the others mirror; argv[3] = split length)
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -32,6 +35,35 @@ struct Node { Box box; int l = -1, r = -1; int first = 0, count = 0; };   // lea
 
 static std::vector<Tri> tris;
 static std::vector<Box> tbox;
+static std::vector<int> origid;
+static float split_len = 0;   // references longer than this along an axis are split
+static int split_max_depth = 8;
+// clip polygon against axis plane
+static std::vector<V> clipPoly(const std::vector<V>& p, int ax, float pos, bool keep_less) {
+    std::vector<V> out; size_t n = p.size();
+    for (size_t i = 0; i < n; ++i) {
+        V a = p[i], b = p[(i + 1) % n]; float da = (&a.x)[ax] - pos, db = (&b.x)[ax] - pos;
+        bool ia = keep_less ? da <= 0 : da >= 0, ib = keep_less ? db <= 0 : db >= 0;
+        if (ia) out.push_back(a);
+        if (ia != ib) { float t = da / (da - db); V c = a + (b - a) * t; (&c.x)[ax] = pos; out.push_back(c); }
+    }
+    return out;
+}
+static void split_ref(const std::vector<V>& poly, const Box& clipbox, int depth, std::vector<Box>& out) {
+    Box b; for (auto& p : poly) b.grow(p);
+    // intersect with clipbox
+    b.lo = {std::max(b.lo.x, clipbox.lo.x), std::max(b.lo.y, clipbox.lo.y), std::max(b.lo.z, clipbox.lo.z)};
+    b.hi = {std::min(b.hi.x, clipbox.hi.x), std::min(b.hi.y, clipbox.hi.y), std::min(b.hi.z, clipbox.hi.z)};
+    V d = b.hi - b.lo; int ax = d.x > d.y ? (d.x > d.z ? 0 : 2) : (d.y > d.z ? 1 : 2);
+    float len = (&d.x)[ax];
+    if (depth >= split_max_depth || len <= split_len) { out.push_back(b); return; }
+    float pos = (&b.lo.x)[ax] + len * 0.5f;
+    auto L = clipPoly(poly, ax, pos, true), R = clipPoly(poly, ax, pos, false);
+    Box bl = b, br = b; (&bl.hi.x)[ax] = pos; (&br.lo.x)[ax] = pos;
+    if (L.size() >= 3) split_ref(L, bl, depth + 1, out);
+    if (R.size() >= 3) split_ref(R, br, depth + 1, out);
+}
+
 
 // ---------------- builders: all return a BVH2 over `order` (a permutation of primitive ids) ----------------
 struct Bvh2 { std::vector<Node> n; std::vector<int> order; int root = 0; };
@@ -172,9 +204,50 @@ static Bvh2 build_ploc(int R, bool sah_collapse) {
 // ---------------- BVH4 collapse + traversal ----------------
 struct N4 { Box b[4]; int code[4]; /* 0 empty, <0 leaf: -(idx2+1), >0: n4 index */ };
 struct Bvh4 { std::vector<N4> n; const Bvh2* src; };
-static bool greedy4 = false;
+static int greedy4 = 0;
 static Bvh4 collapse4(const Bvh2& t) {
     Bvh4 q; q.src = &t;
+    if (greedy4 == 2) {
+        // DP: cost4[v] = A(v) + min over cuts (<=4 nodes) of sum of child costs; leaf cost = 1.2 * A(v) * count
+        int N = (int)t.n.size();
+        std::vector<double> cost(N, 0.0);
+        std::vector<std::vector<int>> cut(N);
+        // post-order
+        std::vector<int> order; order.reserve(N);
+        { std::vector<int> st{t.root}; while (!st.empty()) { int v = st.back(); st.pop_back(); order.push_back(v); if (t.n[v].l >= 0) { st.push_back(t.n[v].l); st.push_back(t.n[v].r); } } }
+        for (int k = N - 1; k >= 0; --k) {
+            int v = order[k];
+            if (t.n[v].l < 0) { cost[v] = 1.2 * t.n[v].box.area() * t.n[v].count; continue; }
+            // enumerate cuts by BFS expansion: state = list of nodes; expand any internal node while size < 4
+            double best = 1e300; std::vector<int> bestc;
+            std::function<void(std::vector<int>&, size_t)> rec = [&](std::vector<int>& c, size_t start) {
+                double sum = 0; for (int x : c) sum += cost[x];
+                if (sum < best) { best = sum; bestc = c; }
+                if (c.size() >= 4) return;
+                for (size_t i = start; i < c.size(); ++i) {
+                    int x = c[i]; if (t.n[x].l < 0) continue;
+                    std::vector<int> d = c; d[i] = t.n[x].l; d.push_back(t.n[x].r);
+                    rec(d, i);
+                }
+            };
+            std::vector<int> c0{t.n[v].l, t.n[v].r};
+            rec(c0, 0);
+            cost[v] = t.n[v].box.area() * 1.0 + best;
+            cut[v] = bestc;
+        }
+        std::function<int(int)> rec2 = [&](int c) -> int {
+            int id = (int)q.n.size(); q.n.emplace_back(); for (int k = 0; k < 4; ++k) q.n[id].code[k] = 0;
+            std::vector<int> ent = t.n[c].l < 0 ? std::vector<int>{c} : cut[c];
+            for (size_t k = 0; k < ent.size(); ++k) {
+                q.n[id].b[k] = t.n[ent[k]].box;
+                if (t.n[ent[k]].l < 0) q.n[id].code[k] = -(ent[k] + 1);
+                else { int ci = rec2(ent[k]); q.n[id].code[k] = ci; }
+            }
+            return id;
+        };
+        rec2(t.root);
+        return q;
+    }
     if (greedy4) {
         // expand the entry with the largest surface area until four slots are filled
         std::function<int(int)> rec = [&](int c) -> int {
@@ -257,7 +330,21 @@ int main(int argc, char** argv) {
     FILE* f = fopen(argv[1], "rb"); std::vector<float> buf; float tmp[9];
     while (fread(tmp, 4, 9, f) == 9) { tris.push_back({{tmp[0], tmp[1], tmp[2]}, {tmp[3], tmp[4], tmp[5]}, {tmp[6], tmp[7], tmp[8]}}); }
     fclose(f);
-    for (auto& t : tris) { Box b; b.grow(t.a); b.grow(t.b); b.grow(t.c); tbox.push_back(b); }
+    if (argc > 3) split_len = atof(argv[3]);
+    {
+        std::vector<Tri> nt; int id = 0;
+        for (auto& t : tris) {
+            Box b; b.grow(t.a); b.grow(t.b); b.grow(t.c);
+            if (split_len > 0) {
+                std::vector<Box> parts; Box inf; inf.lo = {-1e30f,-1e30f,-1e30f}; inf.hi = {1e30f,1e30f,1e30f};
+                split_ref({t.a, t.b, t.c}, inf, 0, parts);
+                for (auto& pb : parts) { nt.push_back(t); tbox.push_back(pb); origid.push_back(id); }
+            } else { nt.push_back(t); tbox.push_back(b); origid.push_back(id); }
+            ++id;
+        }
+        printf("%zu refs from %zu tris\n", nt.size(), tris.size());
+        tris.swap(nt);
+    }
     printf("%zu triangles\n", tris.size());
     struct Cfg { const char* name; Bvh2 t; };
     std::vector<Cfg> cfgs;
@@ -270,12 +357,12 @@ int main(int argc, char** argv) {
     // camera of main.rs at 4K, every 6th pixel
     V orig{2.28125f, -0.5f, 0.f}, cam{2.f, 0.f, -0.5f}, vu{0, 1, 0}, vv{-0.5625f, 0, 0};
     int W = 3840, H = 2160;
-    for (int pass = 0; pass < 2; ++pass)
+    for (int pass = 0; pass < 3; ++pass)
     for (auto& c : cfgs) {
-        greedy4 = pass == 1;
-        if (greedy4) printf("[greedy BVH4 collapse] ");
+        greedy4 = pass;
+        if (greedy4 == 1) printf("[greedy BVH4 collapse] "); if (greedy4 == 2) printf("[DP BVH4 collapse] ");
         Bvh4 q = collapse4(c.t);
-        Cnt prim, bnc; std::mt19937 rng(1); std::uniform_real_distribution<float> U(-0.5f, 0.5f);
+        Cnt prim, bnc, bnd, bnt; std::mt19937 rng(1); std::uniform_real_distribution<float> U(-0.5f, 0.5f);
         int nleaf = 0, maxleaf = 0; for (auto& n : c.t.n) if (n.l < 0) { nleaf++; maxleaf = std::max(maxleaf, n.count); }
         for (int r = 0; r < H; r += 12) for (int col = 0; col < W; col += 12) {
             V p = orig + vu * ((col + 0.5f) / W) + vv * ((r + 0.5f) / H); V d = unit(p - cam); float t;
@@ -284,12 +371,13 @@ int main(int argc, char** argv) {
             while (h >= 0 && depth < 5) {   // bounce: teapot (h < 6320) lambertian, disks mirror
                 V hp = p + d * t; const Tri& tr = tris[h]; V n = unit(cross(tr.b - tr.a, tr.c - tr.a)); if (dot(n, d) > 0) n = n * -1.f;
                 V nd;
-                if (h < lamb_below) { V rv = unit(V{U(rng), U(rng), U(rng)}); nd = unit(n + rv); } else nd = unit(d - n * (2.f * dot(d, n)));
-                p = hp + nd * 0.001f; d = nd; h = trace(q, p, d, t, bnc); depth++;
+                if (origid[h] < lamb_below) { V rv = unit(V{U(rng), U(rng), U(rng)}); nd = unit(n + rv); } else nd = unit(d - n * (2.f * dot(d, n)));
+                bool fromdisk = origid[h] >= lamb_below; p = hp + nd * 0.001f; d = nd; { Cnt one; h = trace(q, p, d, t, one); bnc.nodes += one.nodes; bnc.tris += one.tris; bnc.rays++; Cnt& w = fromdisk ? bnd : bnt; w.nodes += one.nodes; w.tris += one.tris; w.rays++; } depth++;
             }
         }
         printf("%-30s nodes2 %5zu leaves %4d maxleaf %d n4 %4zu SAH %.1f | primary: %.2f visits %.2f tris | bounce (%.0f rays): %.2f visits %.2f tris\n", c.name, c.t.n.size(), nleaf, maxleaf,
                q.n.size(), sah(c.t), prim.nodes / prim.rays, prim.tris / prim.rays, bnc.rays, bnc.nodes / bnc.rays, bnc.tris / bnc.rays);
+        printf("      from disk (%.0f): %.2f visits %.2f tris | from teapot (%.0f): %.2f visits %.2f tris\n", bnd.rays, bnd.nodes / bnd.rays, bnd.tris / bnd.rays, bnt.rays, bnt.nodes / bnt.rays, bnt.tris / bnt.rays);
     }
     return 0;
 }
