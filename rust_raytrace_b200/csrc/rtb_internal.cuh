@@ -53,6 +53,7 @@ struct SceneDev {
 // stream: 3.65 ms of device time), so more pieces is not better.
 #define RTB_DEFAULT_PIECES 8          /* rtb_render: more pieces = earlier D2H overlap */
 #define RTB_DEFAULT_PIECES_DEVICE 1   /* rtb_render_device: no copies to overlap */
+#define RTB_DEFAULT_PIECES_RGB8 3     /* rtb_render_rgb8: 3 B/px go home, the copy is short */
 #define RTB_DEFAULT_LANES 2
 
 // Image tiling: one CTA = 128 threads = 16 x 8 pixels; one warp = 8 x 4 pixels.
