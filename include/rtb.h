@@ -93,11 +93,16 @@ enum {
                                  default wavefront pipeline (rtb_wavefront.cu); same results        */
     RTB_FLAG_TIMING   = 16u,  /* rtb_render_device only: bracket every pipeline stage with CUDA events on the
                                  launching stream and report RtbStats.ms_stage (one piece, one lane)  */
-    RTB_FLAG_POOL     = 32u   /* A/B: bounce kernel variant with a shared-memory pool of 64 rays per warp (fuller
-                                 warps, more state traffic; rtb_wavefront.cu); same results              */
+    RTB_FLAG_RESERVED32 = 32u, /* was RTB_FLAG_POOL (round 1's shared-memory ray-pool bounce kernel, measured slower and
+                                 removed); ignored                                   */
+    RTB_FLAG_FUSED    = 64u   /* A/B: primary phase and bounce phase of the path kernel as ONE launch per sample (the bounce
+                                 phase consumes the queue while the primary phase still fills it) instead of two; same
+                                 results, measured 5 % slower on one GPU and equal on a 1/8 share      */
 };
 
-/* Pipeline stages of the wavefront renderer, indices into RtbStats.ms_stage. */
+/* Stage timers of the wavefront renderer, indices into RtbStats.ms_stage: the primary phase of the path kernel (ray
+ * generation, traversal, shading of the primary hits) is RTB_STAGE_TRACE, the bounce phase RTB_STAGE_BOUNCE (with
+ * RTB_FLAG_FUSED the one launch is reported under RTB_STAGE_TRACE).  RAYGEN and SHADE are no separate kernels any more. */
 enum { RTB_STAGE_RAYGEN = 0, RTB_STAGE_TRACE = 1, RTB_STAGE_SHADE = 2, RTB_STAGE_BOUNCE = 3, RTB_N_STAGES = 4 };
 
 typedef struct RtbStats {

@@ -340,6 +340,57 @@ def main_scene_tris(verts, faces, deterministic=False):
     return np.concatenate(parts)
 
 
+def load_mesh_bin(path=None):
+    """Reader of the committed mesh fixture (rust_raytrace_b200/data/teapot_mesh.bin = raytrace/teapot_tri.obj parsed by
+    tests/golden/make_fixtures.py): b"RTBM", u32 n_verts, u32 n_faces, f32 verts[n][3], u32 faces[n][3] (1-based)."""
+    import struct
+    if path is None:
+        path = os.path.join(os.path.dirname(_HERE), "rust_raytrace_b200", "data", "teapot_mesh.bin")
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    assert raw[:4] == b"RTBM"
+    nv, nf = struct.unpack_from("<II", raw, 4)
+    verts = np.frombuffer(raw, "<f4", nv * 3, 12).reshape(nv, 3).copy()
+    faces = np.frombuffer(raw, "<u4", nf * 3, 12 + nv * 12).reshape(nf, 3).copy()
+    return verts, faces
+
+
+def teapot_field_tris(verts, faces, nz=12, ny=13, seed=1, scale=0.3):
+    """BASELINE config 4: nz x ny teapots on a grid receding from main.rs's camera, every instance with
+    its own roll angle from a Numerical-Recipes LCG, `Reflective{scattering: 0}` surfaces.  Same definition as the product
+    package's teapot_field_scene (tests/test_host.py compares the bytes)."""
+    surf = Surface(OR_REFLECTIVE, make_color(252, 119, 0), 0.5, 0.0)
+    parts = [make_dummy_triangle()]
+    state = int(seed) & 0xFFFFFFFF
+    for iz in range(nz):
+        for iy in range(ny):
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+            roll = 270.0 + 360.0 * (state >> 8) / float(1 << 24)
+            tf = create_transform(unit([0.0, 0.3, 1.0]), to_radians(roll))
+            off = [-1.2, (iy - (ny - 1) / 2.0) * 2.2, 3.0 + 2.0 * iz]
+            parts.append(mesh_to_triangles(verts, faces, off, scale, tf, surf, 0.05))
+    return np.concatenate(parts)
+
+
+def circles_scene_parts(n=64, seed=1, light=((6.0, -1.0, 2.0), 0.6)):
+    """BASELINE config 1 as this build defines it (EXTENSION): (tris, spheres, light) — n analytic
+    spheres of random colour (one in eight a mirror, one in eight matte) over a matte ground disk, one cube light.  Same
+    definition as the product package's circles_scene (tests/test_host.py compares the bytes)."""
+    rng = np.random.RandomState(seed)
+    sph = np.zeros(n, SPH_DTYPE)
+    for k in range(n):
+        c = [float(rng.uniform(-0.5, 3.5)), float(rng.uniform(-5.0, 5.0)), float(rng.uniform(4.0, 14.0))]
+        col = make_color(*[int(x) for x in rng.randint(30, 255, 3)])
+        kind, alpha = (OR_REFLECTIVE, 0.6) if k % 8 == 0 else ((OR_MATTE, 0.3) if k % 8 == 1 else (OR_SOLID, 0.0))
+        sph[k]["center"] = c
+        sph[k]["radius"] = float(rng.uniform(0.25, 0.7))
+        sph[k]["kind"], sph[k]["alpha"], sph[k]["scattering"] = kind, alpha, 0.0
+        sph[k]["color"] = col
+    ground = make_disk([-1.5, 0.0, 9.0], unit([1.0, 0.0, 0.05]), 9.0, 0.1, 40,
+                       Surface(OR_MATTE, make_color(150, 150, 150), 0.25), Surface(OR_SOLID, [0.1, 0.1, 0.1]), -1.0)
+    return np.concatenate([make_dummy_triangle(), ground]), sph, light
+
+
 def main_viewport(width, height, maxdepth=5, spp=1) -> OrView:
     """main.rs:166-173 with aspect = height/width (main.rs:96-110)."""
     aspect = np.float32(height) / np.float32(width)

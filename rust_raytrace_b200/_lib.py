@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("RTB_LIB", os.path.join(_PKG, "librtb.so"))   # RTB_LI
 
 RTB_OK, RTB_ERR_NO_DEVICE, RTB_ERR_CUDA, RTB_ERR_INVALID, RTB_ERR_NOMEM = 0, -1, -2, -3, -4
 RTB_SOLID, RTB_MATTE, RTB_REFLECTIVE = 0, 1, 2
-RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL, RTB_FLAG_TIMING, RTB_FLAG_POOL = 1, 2, 4, 8, 16, 32
+RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL, RTB_FLAG_TIMING, RTB_FLAG_FUSED = 1, 2, 4, 8, 16, 64
 RTB_STAGES = ("raygen", "trace", "shade", "bounce")
 RTB_MAX_DEPTH = 16
 

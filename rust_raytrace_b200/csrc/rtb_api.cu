@@ -186,13 +186,15 @@ int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd
     if (vd.flags & RTB_FLAG_MEGAKERNEL)
         return rtb_launch_trace(scene_dev(g, n_prims), vd, d_rgba, d_prim, d_t, g.d_counters, st, launches);
     const uint32_t n_slots = vd.my_tile_rows * 2u * ((vd.width + 7u) / 8u) * 32u;
-    const size_t need = rtb_wf_workspace_bytes(n_slots, vd.maxdepth ? vd.maxdepth : 1, (vd.s_end - vd.s_begin) > 1,
-                                               scene_dev(g, n_prims).stack4, vd.flags);
+    const size_t need = rtb_wf_workspace_bytes(n_slots, vd.maxdepth ? vd.maxdepth : 1, (vd.s_end - vd.s_begin) > 1);
     if (lane.ws_bytes < need) {
         RTB_CUDA(cudaDeviceSynchronize());
         if (lane.d_ws) RTB_CUDA(cudaFree(lane.d_ws));
-        lane.d_ws = nullptr; lane.ws_bytes = 0;
+        lane.d_ws = nullptr; lane.ws_bytes = 0; lane.epoch = 0;
         RTB_CUDA(cudaMalloc(&lane.d_ws, need + need / 16));     // slack: pieces differ by a band
+        // the bounce queue's tag words start as "no launch"; on the LAUNCHING stream: a null-stream memset is not ordered
+        // before kernels on a non-blocking stream and would wipe entries of the running frame
+        RTB_CUDA(cudaMemsetAsync(lane.d_ws, 0, need + need / 16, st));
         lane.ws_bytes = need + need / 16;
     }
     *primary_rays += owned_pixels(vd) * (uint64_t)(vd.s_end - vd.s_begin);
@@ -201,8 +203,8 @@ int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd
         for (auto& e : lane.stage_ev) if (!e) RTB_CUDA(cudaEventCreate(&e));
         sev = lane.stage_ev;
     }
-    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, lane.d_ws, d_rgba, d_prim, d_t, g.d_counters, st, launches,
-                                sev, lane.stage_ms);
+    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, lane.d_ws, &lane.epoch, d_rgba, d_prim, d_t, g.d_counters, st,
+                                launches, sev, lane.stage_ms);
 }
 
 int env_int(const char* name, int dflt) {
@@ -655,6 +657,7 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
         RTB_CUDA(cudaStreamSynchronize(st));
         float ms = 0.f;
         RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        if (c.stalled) return fail(RTB_ERR_CUDA, "path kernel watchdog: a reserved bounce-queue entry never arrived");
         std::memset(stats, 0, sizeof *stats);
         stats->rays = c.rays + primary; stats->node_tests = c.node_tests; stats->tri_tests = c.tri_tests;
         stats->bounce_rays = c.rays; stats->node_tests_bounce = c.node_tests_bounce; stats->tri_tests_bounce = c.tri_tests_bounce;
@@ -795,6 +798,7 @@ int render_host(rtb_scene* s, const RtbView* view, float* rgba_out, uint8_t* rgb
     for (uint32_t r = 0; r < world; ++r) {
         launches += launches_r[r]; primary_total += primary_r[r];
         const TraceCounters& c = cnt_r[r];
+        if (c.stalled) return fail(RTB_ERR_CUDA, "path kernel watchdog: a reserved bounce-queue entry never arrived");
         st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
         st.bounce_rays += c.rays; st.node_tests_bounce += c.node_tests_bounce; st.tri_tests_bounce += c.tri_tests_bounce;
         st.ms_render = std::max(st.ms_render, (double)ms_r[r]);
@@ -895,6 +899,7 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
         RTB_CUDA(cudaMemcpy(&c, g.d_counters, sizeof c, cudaMemcpyDeviceToHost));
         float ms = 0.f;
         RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        if (c.stalled) return fail(RTB_ERR_CUDA, "path kernel watchdog: a reserved bounce-queue entry never arrived");
         st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
         st.bounce_rays += c.rays; st.node_tests_bounce += c.node_tests_bounce; st.tri_tests_bounce += c.tri_tests_bounce;
         st.ms_render = std::max(st.ms_render, (double)ms);

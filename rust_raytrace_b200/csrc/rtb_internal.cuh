@@ -89,6 +89,7 @@ struct TraceCounters {
     unsigned long long tri_tests;
     unsigned long long node_tests_bounce;   // share of the two above spent in k_wf_bounce
     unsigned long long tri_tests_bounce;
+    unsigned long long stalled;             // fused path kernel: watchdog trips (0 unless something is badly wrong)
 };
 
 // One compute lane of a GPU: a stream with its own wavefront workspace (ray queues, hit records, mix stacks, RNG).
@@ -97,6 +98,7 @@ struct GpuLane {
     cudaEvent_t done = nullptr;
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
+    uint32_t epoch = 0;            // launches of the path kernel on this workspace (the bounce queue's entry tag)
     cudaEvent_t stage_ev[RTB_N_STAGES + 1] = {};   // RTB_FLAG_TIMING: stage boundaries of one sample
     float stage_ms[RTB_N_STAGES] = {};
 };
@@ -183,13 +185,14 @@ int rtb_launch_trace(const SceneDev& sc, const ViewDev& vw, float4* d_rgba, uint
 int rtb_launch_trace_ext(const SceneDev& sc, const ViewDev& vw, const ExtParams& ex, float4* d_rgba, uint32_t* d_prim,
                          float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches);
 // ---- implemented in rtb_wavefront.cu -------------------------------------------
-// The default renderer: raygen / persistent trace / shade+compact stages per bounce level.
+// The default renderer: one persistent kernel per sample (primary phase + bounce phase, rtb_wavefront.cu).
 // counters->rays receives the BOUNCE rays only; the caller adds the primary rays (valid pixels x samples).
-size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample, uint32_t stack4, uint32_t flags);
+// workspace: rtb_wf_workspace_bytes, ZERO-FILLED when allocated; epoch: the workspace's launch counter (queue entry tags).
+size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample);
 // stage_ev (nullable): 5 events recorded at the stage boundaries of every sample; stage_ms accumulates their gaps
 // (this synchronises the stream once per sample: timing mode only).
-int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace, float4* d_rgba, uint32_t* d_prim,
-                         float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches,
+int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace, uint32_t* epoch, float4* d_rgba,
+                         uint32_t* d_prim, float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches,
                          cudaEvent_t* stage_ev = nullptr, float* stage_ms = nullptr);
 
 int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream);

@@ -154,21 +154,41 @@ def test_megakernel_equals_wavefront(R, O, scenes, spp):
     assert_bit_exact(b, bvh.render(O.main_viewport(801, 453, 5, spp), seed=13), f"megakernel spp={spp}")
 
 
-@pytest.mark.parametrize("spp,maxdepth", [(1, 5), (2, 16)])
-def test_pool_bounce_kernel_equals_default(R, O, scenes, spp, maxdepth):
-    """The shared-memory ray-pool variant of the bounce kernel (RTB_FLAG_POOL) is the same function as the default
-    register-resident one: ids, t, colour, ray and test counts; and it matches the oracle."""
+@pytest.mark.parametrize("spp,maxdepth,wh", [(1, 5, (1283, 721)), (3, 16, (640, 363)), (1, 1, (333, 217)), (2, 2, (17, 9))])
+def test_fused_launch_equals_the_two_phase_launches(R, O, scenes, spp, maxdepth, wh):
+    """The path kernel runs its primary phase and its bounce phase as two launches per sample.  RTB_FLAG_FUSED runs both in
+    ONE launch whose bounce phase consumes the queue its primary phase is still filling (tagged entries + tickets, no
+    kernel boundary): ids, t, colour, ray and test counts must be identical, and both must match the oracle."""
     from rust_raytrace_b200 import _lib
     s, _, bvh = scenes[False]
-    v = R.main_viewport(1283, 721, maxdepth, spp)
-    a = gpu_render(R, s, v, seed=17, stats=True)
-    vp = _lib.RtbView.from_buffer_copy(v)
-    vp.flags |= _lib.RTB_FLAG_POOL
-    b = gpu_render(R, s, vp, seed=17, stats=True)
+    v = R.main_viewport(*wh, maxdepth, spp)
+    a = gpu_render(R, s, v, seed=23, stats=True)
+    vs = _lib.RtbView.from_buffer_copy(v)
+    vs.flags |= _lib.RTB_FLAG_FUSED
+    b = gpu_render(R, s, vs, seed=23, stats=True)
     assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
     assert a[3].total_rays == b[3].total_rays
     assert a[4].stats.node_tests == b[4].stats.node_tests and a[4].stats.tri_tests == b[4].stats.tri_tests
-    assert_bit_exact(b, bvh.render(O.main_viewport(1283, 721, maxdepth, spp), seed=17), f"pool spp={spp}")
+    assert a[4].stats.node_tests_bounce == b[4].stats.node_tests_bounce
+    assert_bit_exact(b, bvh.render(O.main_viewport(*wh, maxdepth, spp), seed=23), f"fused {wh} spp={spp} maxdepth={maxdepth}")
+
+
+def test_fused_kernel_is_repeatable(R, scenes):
+    """Twenty frames through the fused launch on one scene handle (the queue is never cleared: every launch has its own
+    entry tag) — every frame identical, and identical again after a differently sized frame reused the workspace."""
+    from rust_raytrace_b200 import _lib
+    s = scenes[False][0]
+    v = R.main_viewport(960, 541, 5, 1)
+    v.flags |= _lib.RTB_FLAG_FUSED
+    first = gpu_render(R, s, v, seed=4)
+    for k in range(20):
+        if k == 10:
+            v2 = R.main_viewport(400, 300, 5, 2)
+            v2.flags |= _lib.RTB_FLAG_FUSED
+            gpu_render(R, s, v2, seed=1)
+        again = gpu_render(R, s, v, seed=4)
+        assert np.array_equal(bits(first[0]), bits(again[0])) and np.array_equal(first[1], again[1])
+        assert first[3].total_rays == again[3].total_rays
 
 
 def test_rotated_camera(R, O, scenes):

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rust_raytrace_b200 as R
 from rust_raytrace_b200 import _lib
 s = R.main_scene(False)
-for flags in (0, _lib.RTB_FLAG_STATS, _lib.RTB_FLAG_POOL, _lib.RTB_FLAG_MEGAKERNEL, _lib.RTB_FLAG_BRUTE):
+for flags in (0, _lib.RTB_FLAG_STATS, _lib.RTB_FLAG_FUSED, _lib.RTB_FLAG_MEGAKERNEL, _lib.RTB_FLAG_BRUTE):
     for spp in (1, 2):
         v = R.main_viewport(48, 40, 5, spp)
         v.flags = flags

@@ -8,7 +8,7 @@ L = _lib.lib()
 _lib.check(L.rtb_init(1, None), "init")
 scene = R.main_scene(False); h = scene.upload()
 MD = int(os.environ.get("MAXDEPTH", "5"))
-v = R.main_viewport(3840, 2160, MD, 1); v.seed = 7; v.flags = _lib.RTB_FLAG_TIMING
+v = R.main_viewport(3840, 2160, MD, 1); v.seed = 7; v.flags = _lib.RTB_FLAG_TIMING | int(os.environ.get("FLAGS", "0"))      # FLAGS=64: RTB_FLAG_FUSED
 d = torch.zeros((2160, 3840, 4), dtype=torch.float32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
