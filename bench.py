@@ -4,16 +4,20 @@
 Workload (BASELINE.json configs[2], the one the metric is quoted on): the main.rs scene
 (teapot mesh 6,320 triangles + two 200-triangle mirror disks + dummy = 6,721 `Triangle`s) at
 3840x2160, maxdepth 5, 1 spp, shipped materials (Matte teapot, fuzzy Reflective disks).
-A "step" is one full frame: primary-ray generation, LBVH traversal, exact ray/triangle tests,
+A "step" is one full frame: primary-ray generation, BVH traversal, exact ray/triangle tests,
 bounce shading and accumulation for all 8,294,400 pixels (~14.26 M rays).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # one JSON line (rank 0)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...                            # CPU reference arm (oracle port)
 
-value   : Mrays/s, frame rendered into a device-resident buffer (inputs resident in HBM), CUDA events
-          on the launching stream, max over ranks; rays = project_ray calls with depth>0
-          (the reference's own counter, raytrace.rs:1278), summed over ranks.
+value   : Mrays/s of a COMPLETE frame resident on GPU 0.  At N > 1 (one process per GPU) every rank renders its
+          8-row bands straight into rank 0's frame buffer (CUDA IPC mapping, stores over NVLink peer access); the
+          timed region of a rank is its own stream, CUDA events, max over ranks; rays = project_ray calls with
+          depth>0 (the reference's own counter, raytrace.rs:1278), summed over ranks.
+parity  : outside the timed region, the frame the timed steps produced is hashed on rank 0 and compared with the
+          committed golden hash (the CPU oracle's frame, tests/golden/frame_hashes.json) and, at N > 1, with a
+          single-GPU render of the same frame; a mismatch makes the run fail.
 e2e     : same metric through the public API B200RayCaster.walk_rays (-> rtb_render) with HOST
           buffers: per step the view goes H2D as kernel parameters and the whole W*H*16-byte image
           comes back D2H into pinned host memory, inside the timed region.  One process drives all N
@@ -23,6 +27,8 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -54,9 +60,12 @@ WORKLOADS = {
     "progressive8k": ("8K progressive, main.rs scene, 7680x4320, maxdepth 5, 64 spp, samples partitioned over ranks + "
                       "NCCL reduce(sum) of the f32 accumulation buffers + 1/spp", 7680, 4320, 5, 64, "samples"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_wf_bounce launch of the teapot4k frame at N=1, from the
-# `ncu --set full` capture summarised in profiles/ (see DESIGN.md "Roofline"); null for every other configuration.
-NCU_TRAFFIC_BOUNCE_TEAPOT4K = 371.7e6   # profiles/r1_v10_k_wf_bounce_raw.csv: 258.7 MB read + 113.0 MB written
+
+
+def workload_config(name):
+    """The `config` object of the JSON line — identical in the GPU arm and the reference arm."""
+    desc, W, H, maxdepth, spp, partition = WORKLOADS[name]
+    return {"workload": desc, "name": name, "width": W, "height": H, "maxdepth": maxdepth, "spp": spp, "seed": SEED}
 
 
 def measured_peaks():
@@ -66,6 +75,26 @@ def measured_peaks():
         return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_dram_traffic(name, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the newest `ncu --set full`
+    summary under profiles/ (written by tools/summarize_profiles.sh for the teapot4k frame at N=1); None for every other
+    configuration.  Returns (bytes, source file)."""
+    if name != "teapot4k" or world != 1:
+        return None, None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_wf_path_bounce_raw.csv")), key=os.path.getmtime)
+    if not files:
+        return None, None
+    tot, seen = 0.0, 0
+    for ln in open(files[-1]):
+        f = ln.strip().split(",")
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[1], None)
+            if scale is not None:
+                tot += float(f[2]) * scale
+                seen += 1
+    return (tot, os.path.relpath(files[-1], ROOT)) if seen == 2 else (None, None)
 
 
 class ClockSampler:
@@ -118,41 +147,40 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU reference arm (the oracle restatement running the reference's octree algorithm)
+# CPU reference arm: the oracle restatement running the reference's octree algorithm.  Nothing of the product package
+# is imported here: the scenes come from oracle.py's own generators (tests/test_host.py compares their bytes with the
+# product's), so the only native code this arm loads is oracle/build/liboracle.so.
 # --------------------------------------------------------------------------------------------
-def build_scene(R, name):
-    if name == "circles2k":
-        return R.circles_scene()
-    return R.teapot_field_scene() if name == "field1m" else R.main_scene(deterministic=False)
-
-
-def oracle_scene(O, scene, name, cores):
+def oracle_scene(O, name, cores):
     """Reference-algorithm mode (octree) wherever the reference's builder can handle the scene; the 1M-triangle
     scene cannot be built as an octree in reasonable time, there the oracle uses its own BVH."""
+    verts, faces = O.load_mesh_bin()
     accel = O.ACCEL_BVH if name == "field1m" else O.ACCEL_OCTREE
-    osc = O.Scene(scene.tris.view(O.TRI_DTYPE), accel, build_threads=cores)
-    if getattr(scene, "spheres", None) is not None:
-        osc.add_spheres(scene.spheres.view(O.SPH_DTYPE))
-    if getattr(scene, "light", None) is not None:
-        osc.set_light(*scene.light)
+    if name == "circles2k":
+        tris, spheres, light = O.circles_scene_parts()
+        osc = O.Scene(tris, accel, build_threads=cores).add_spheres(spheres).set_light(*light)
+    elif name == "field1m":
+        osc = O.Scene(O.teapot_field_tris(verts, faces), accel, build_threads=cores)
+    else:
+        osc = O.Scene(O.main_scene_tris(verts, faces, False), accel, build_threads=cores)
     return osc, ("bvh" if accel == O.ACCEL_BVH else "octree")
 
 
-def cpu_reference(name, rows, threads=None, repeat=1):
+def accel_text(accel):
+    return ("reference-algorithm mode (octree 204,894 nodes, row work-queue)" if accel == "octree"
+            else "BVH mode (the reference octree cannot be built for 1M triangles; row work-queue)")
+
+
+def cpu_reference(name, rows, threads=None, scene=None):
     """Times the oracle on image rows [rows[0], rows[1]) of the workload's frame (all samples).
-    Returns (Mrays/s, rays, seconds, cores, accel)."""
+    Returns (Mrays/s, rays, seconds, cores, accel, scene)."""
     from oracle import oracle as O
-    import rust_raytrace_b200 as R   # host-side scene construction only (no GPU use)
     desc, W, H, maxdepth, spp, _ = WORKLOADS[name]
     cores = threads or os.cpu_count() or 1
-    osc, accel = oracle_scene(O, build_scene(R, name), name, cores)   # build excluded, as main.rs:160 vs :191
+    osc, accel = scene if scene else oracle_scene(O, name, os.cpu_count() or 1)   # build excluded, as main.rs:160 vs :191
     ov = O.main_viewport(W, H, maxdepth, spp)
-    best = None
-    for _ in range(repeat):
-        _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
-        if best is None or st.seconds < best[2]:
-            best = (st.rays / st.seconds / 1e6, int(st.rays), float(st.seconds), cores, accel)
-    return best
+    _, _, _, st = osc.render(ov, seed=SEED, threads=cores, rows=rows, want_ids=False)
+    return st.rays / st.seconds / 1e6, int(st.rays), float(st.seconds), cores, accel, (osc, accel)
 
 
 def cpu_sample_rows(name):
@@ -167,16 +195,22 @@ def cpu_sample_rows(name):
     return (H // 2, H // 2 + 4)       # 64 spp: 4 rows x 7680 px x 64 samples
 
 
+def cpu_one_thread_rows(name):
+    """The 1-thread figure (the reference's `threads` argument, main.rs:191) on a band 1/16 the size."""
+    r0, r1 = cpu_sample_rows(name)
+    mid, n = (r0 + r1) // 2, max(1, (r1 - r0) // 16)
+    return (mid - n // 2, mid - n // 2 + n)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
-    import rust_raytrace_b200 as R   # host-side scene construction only (no GPU use)
     name = args.workload
     desc, W, H, maxdepth, spp, _ = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    osc, accel = oracle_scene(O, build_scene(R, name), name, cores)
+    osc, accel = oracle_scene(O, name, cores)
     ov = O.main_viewport(W, H, maxdepth, spp)
     # bounded sample per step, sized so that warmup+steps stay within a few minutes whatever the host:
     # ~2 s of work at the rate of a small probe band through the middle of the frame
@@ -194,13 +228,13 @@ def run_reference(args):
         if i >= args.warmup:
             rates.append(st.rays / st.seconds / 1e6); secs.append(st.seconds)
     value = float(np.mean(rates))
-    sample = (f"image rows {rows[0]}..{rows[1]} of {H} ({rays} rays per step), oracle in "
-              f"{'reference-algorithm mode (octree 204,894 nodes, row work-queue)' if accel == 'octree' else 'BVH mode (row work-queue)'}")
+    sample = f"image rows {rows[0]}..{rows[1]} of {H} ({rays} rays per step), oracle in {accel_text(accel)}"
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "sample": f"rows {rows[0]}..{rows[1]} of {H} per step"},
+        "config": workload_config(name),
+        "details": {"sample": f"rows {rows[0]}..{rows[1]} of {H} per step", "rays_per_step": rays},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -210,6 +244,19 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def build_scene(R, name):
+    if name == "circles2k":
+        return R.circles_scene()
+    return R.teapot_field_scene() if name == "field1m" else R.main_scene(deterministic=False)
+
+
+class DevFrame:
+    """A raw device allocation (rtb_device_alloc or an IPC mapping of one) seen by torch without a copy."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -253,7 +300,26 @@ def run_gpu(args):
         my_view = view
         tile_rank, tile_world = rank, world
 
-    d_rgba = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    # The frame.  Bands over N > 1 processes: ONE frame buffer on rank 0's GPU, mapped into every other rank with CUDA IPC;
+    # each rank's kernels store their bands into it over NVLink.  Samples over ranks: every rank owns a full sum buffer
+    # and NCCL reduces them to rank 0.
+    shared_frame = world > 1 and not by_samples
+    frame_ptr = C.c_void_p()
+    if shared_frame:
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            _lib.check(L.rtb_device_alloc(0, npix * 16, C.byref(frame_ptr)), "rtb_device_alloc")
+            hbuf = C.create_string_buffer(64)
+            _lib.check(L.rtb_ipc_export(frame_ptr, hbuf), "rtb_ipc_export")
+            handle.copy_(torch.tensor(list(hbuf.raw), dtype=torch.uint8))
+        dist.broadcast(handle, 0)
+        if rank != 0:
+            _lib.check(L.rtb_ipc_open(0, bytes(handle.cpu().tolist()), C.byref(frame_ptr)), "rtb_ipc_open")
+        d_rgba = torch.as_tensor(DevFrame(frame_ptr.value, (H, W, 4)), device="cuda") if rank == 0 else None
+        d_rgba_ptr = frame_ptr.value
+    else:
+        d_rgba = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        d_rgba_ptr = d_rgba.data_ptr()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     # an explicit (non-null) stream: handle 0 would mean "the library's own stream" to rtb_render_device,
     # and torch.cuda.Event only sees the stream it is recorded on
@@ -262,10 +328,10 @@ def run_gpu(args):
     assert stream.cuda_stream != 0
     sp = C.c_void_p(stream.cuda_stream)
 
-    def render(v, stats=None):
+    def render(v, stats=None, ptr=None, tr=None, tw=None):
         if v is not None:
-            _lib.check(L.rtb_render_device(h, C.byref(v), 0, tile_rank, tile_world, d_rgba.data_ptr(), None, None, sp,
-                                           stats), "rtb_render_device")
+            _lib.check(L.rtb_render_device(h, C.byref(v), 0, tile_rank if tr is None else tr, tile_world if tw is None else tw,
+                                           d_rgba_ptr if ptr is None else ptr, None, None, sp, stats), "rtb_render_device")
 
     def step():
         render(my_view)
@@ -281,12 +347,14 @@ def run_gpu(args):
         c.flags |= flags
         return c
 
-    # one counted frame: rays, then (STATS kernel variant) node / triangle tests per ray, per kernel
+    # one counted frame: rays, then (STATS kernel variant) node / triangle tests per ray, per phase
+    scratch = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") if shared_frame else None
+    sptr = scratch.data_ptr() if shared_frame else None
     st = _lib.RtbStats()
-    render(my_view, C.byref(st))
+    render(my_view, C.byref(st), ptr=sptr)
     my_rays = int(st.rays)
     st2 = _lib.RtbStats()
-    render(with_flags(my_view, _lib.RTB_FLAG_STATS), C.byref(st2))
+    render(with_flags(my_view, _lib.RTB_FLAG_STATS), C.byref(st2), ptr=sptr)
 
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
@@ -312,8 +380,8 @@ def run_gpu(args):
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     ms_mine = float(np.mean(ms_steps))
 
-    # per-stage device times of the same step, live (CUDA events on the launching stream between the kernels),
-    # still under the clock sampler; used for the roofline of the dominant kernel
+    # per-phase device times of the same step, live (CUDA events on the launching stream between the two launches of the
+    # path kernel), still under the clock sampler; used for the roofline of the dominant launch
     stage_ms = np.zeros(4)
     n_timing = 0
     if my_view is not None:
@@ -321,7 +389,7 @@ def run_gpu(args):
         tv = with_flags(my_view, _lib.RTB_FLAG_TIMING)
         for _ in range(5):
             flush.fill_(0)
-            render(tv, C.byref(stt))
+            render(tv, C.byref(stt), ptr=sptr)
             stage_ms += np.array(stt.ms_stage[:])
             n_timing += 1
         stage_ms /= n_timing
@@ -335,6 +403,43 @@ def run_gpu(args):
     else:
         ms_step, total_rays = ms_mine, float(my_rays)
     value = total_rays / (ms_step * 1e-3) / 1e6
+
+    # ---- parity of the frame the timed steps left on rank 0's GPU (outside the timed region) ----
+    parity = None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        frame_host = d_rgba.cpu().numpy()
+        parity = {"checked": True, "frame_sha": hashlib.sha256(np.ascontiguousarray(frame_host).tobytes()).hexdigest(),
+                  "frame_on": "GPU 0" + (" (written by all ranks over NVLink peer mappings)" if shared_frame else "")}
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "frame_hashes.json")) as fh:
+                gold = json.load(fh)["frames"].get(name)
+        except Exception:
+            gold = None
+        if gold is not None and not by_samples:
+            parity["golden_sha"] = gold["sha256"]
+            parity["equals_golden"] = parity["frame_sha"] == gold["sha256"] and int(total_rays) == int(gold["rays"])
+            parity["golden"] = "CPU oracle frame, tests/golden/frame_hashes.json (make_frame_hashes.py)"
+        if world > 1:
+            # the same frame rendered by this GPU alone
+            one = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+            st1 = _lib.RtbStats()
+            render(view, C.byref(st1), ptr=one.data_ptr(), tr=0, tw=1)
+            torch.cuda.synchronize()
+            if by_samples:        # the summation order differs (sum of per-rank partial sums): rounding-level differences
+                diff = (one - d_rgba).abs().max().item()
+                mse = ((one - d_rgba) ** 2).mean().item()
+                parity["max_abs_diff_vs_n1"] = diff
+                parity["psnr_vs_n1_db"] = float(10 * np.log10(1.0 / max(mse, 1e-30)))
+                parity["equals_n1"] = bool(diff <= 2e-6)
+            else:
+                parity["equals_n1"] = bool(torch.equal(one.view(torch.int32), d_rgba.view(torch.int32)))
+            parity["rays_equal_n1"] = int(st1.rays) == int(total_rays)
+            del one
+    if world > 1:
+        dist.barrier()
 
     # ---- e2e through the public API with host buffers (rank 0 drives all N GPUs) ----
     e2e = None
@@ -366,7 +471,22 @@ def run_gpu(args):
                "api": ("B200RayCaster.walk_rays_progressive -> rtb_render_progressive" if by_samples else
                        "B200RayCaster.walk_rays -> rtb_render") + " (pinned host image, scene resident)"}
         assert int(caster.stats.rays) == int(total_rays), (caster.stats.rays, total_rays)
+        if parity is not None and not by_samples:
+            parity["e2e_equals_device_frame"] = bool(np.array_equal(data.view(np.uint32), frame_host.view(np.uint32)))
+        if by_samples:
+            e2e["ms_reduce"] = float(getattr(caster.stats, "ms_stage")[2])     # rtb_render_progressive: reduce + D2H phase
         if not by_samples:
+            # the device-to-host floor of the same call: every copy and event of the frame, no kernel (RTB_FLAG_COPY_ONLY)
+            vc = _lib.RtbView.from_buffer_copy(vv)
+            vc.flags |= _lib.RTB_FLAG_COPY_ONLY
+            scratch_host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory().numpy()
+            for _ in range(3):
+                caster.walk_rays(vc, sc_all, scratch_host, threads=args.gpus)
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                caster.walk_rays(vc, sc_all, scratch_host, threads=args.gpus)
+            e2e["d2h_floor_ms"] = (time.perf_counter() - t0) / e_steps * 1e3
+            del scratch_host
             # the same frame the way main.rs consumes it (walk_rays -> write_png): quantised on the device, 3 B/px home
             host8 = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
             rgb = host8.numpy()
@@ -396,66 +516,88 @@ def run_gpu(args):
     if world > 1:
         dist.barrier(group=host_group)
 
+    ok = True
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_src = measured_peaks()
-        # algorithmic bytes / FP32 lane-ops per ray = 32 B, 24 ops per AABB test; 80 B, 54 ops per exact
-        # triangle test; 16 B per output pixel, 45 ops per generated ray.  Dominant kernel = k_wf_bounce (rank 0's launch).
+        # algorithmic FP32 lane-ops / bytes per ray = 24 ops, 32 B per AABB test; 54 ops, 80 B per exact
+        # triangle test; 45 ops per generated ray, 16 B per output pixel.  Dominant launch = the bounce phase of
+        # k_wf_path on rank 0 (for the extension scene the one kernel of rtb_ext.cu, whose tests include the shadow rays').
         n_node, n_tri = st2.node_tests / max(st2.rays, 1), st2.tri_tests / max(st2.rays, 1)
-        if name == "circles2k":      # one kernel per frame (rtb_ext.cu); its tests include the shadow rays'
+        if name == "circles2k":
             dom_kernel, b_rays, nb_node, nb_tri = "k_trace_ext", max(int(st2.rays), 1), n_node, n_tri
             stage_ms = np.array([0.0, 0.0, 0.0, ms_mine])
         else:
-            dom_kernel, b_rays = "k_wf_bounce", max(int(st2.bounce_rays), 1)
+            dom_kernel, b_rays = "k_wf_path<bounce phase>", max(int(st2.bounce_rays), 1)
             nb_node, nb_tri = st2.node_tests_bounce / b_rays, st2.tri_tests_bounce / b_rays
-        bounce_s = max(stage_ms[3], 1e-6) * 1e-3
+        launch_s = max(stage_ms[3], 1e-6) * 1e-3
         bytes_launch = b_rays * (nb_node * 32 + nb_tri * 80 + 16)
         ops_launch = b_rays * (nb_node * 24 + nb_tri * 54 + 45)
         fp32_peak = N_SM * FP32_LANES_PER_SM * sm_max_mhz * 1e6
-        ach_gbs = bytes_launch / bounce_s / 1e9
         step_ops = my_rays * (n_node * 24 + n_tri * 54 + 45)
-        traffic = NCU_TRAFFIC_BOUNCE_TEAPOT4K if (name == "teapot4k" and world == 1) else None
+        traffic, traffic_src = profiled_dram_traffic(name, world)
         cpu = None
         if world == 1 and not args.no_cpu:
             rows = cpu_sample_rows(name)
-            mr, rays, s, cores, accel = cpu_reference(name, rows)
+            mr, rays, s, cores, accel, osc = cpu_reference(name, rows)
+            rows1 = cpu_one_thread_rows(name)
+            mr1, rays1, s1, _, _, _ = cpu_reference(name, rows1, threads=1, scene=osc)
             cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
                    "sample": f"image rows {rows[0]}..{rows[1]} of the same frame ({rays} rays, {s:.1f} s), oracle in "
-                             + ("reference-algorithm mode (octree, row work-queue, all host threads)" if accel == "octree"
-                                else "BVH mode (the reference octree cannot be built for 1M triangles), all host threads")}
+                             + accel_text(accel) + ", all host threads",
+                   "one_thread": {"value": mr1, "unit": "Mrays/s", "cores": 1,
+                                  "sample": f"image rows {rows1[0]}..{rows1[1]} ({rays1} rays, {s1:.1f} s), same oracle, 1 thread"}}
         launches_per_step = int(st.kernel_launches) + (1 if by_samples else 0)
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_frame": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "rays_per_frame": int(total_rays),
-                       "partition": (f"samples: rank r renders samples [64r/{world}, 64(r+1)/{world}) of the full frame, then reduce"
-                                     if by_samples else f"8-row bands, band b -> rank b % {world}"),
-                       "l2": "flushed between timed iterations (256 MiB fill); the scene is re-read from HBM each step",
-                       "bvh": {"nodes": info.n_nodes, "leaves": info.n_leaves, "max_leaf": info.max_leaf,
-                               "height": info.tree_height, "prims": info.n_prims, "refs": info.n_refs,
-                               "ms_build": info.ms_build, "ms_upload": info.ms_upload},
-                       "node_tests_per_ray": n_node, "tri_tests_per_ray": n_tri, "wall_s_timed_region": t_wall},
+            "config": workload_config(name),
+            "details": {"rays_per_frame": int(total_rays),
+                        "partition": (f"samples: rank r renders samples [64r/{world}, 64(r+1)/{world}) of the full frame, then NCCL reduce to rank 0"
+                                      if by_samples else f"8-row bands, band b -> rank b % {world}; every rank stores into the one frame on GPU 0"),
+                        "l2": "flushed between timed iterations (256 MiB fill); the scene is re-read from HBM each step",
+                        "accelerator": os.environ.get("RTB_BVH", "8") + "-wide BVH",
+                        "bvh": {"nodes": info.n_nodes, "leaves": info.n_leaves, "max_leaf": info.max_leaf,
+                                "height": info.tree_height, "prims": info.n_prims, "refs": info.n_refs,
+                                "ms_build": info.ms_build, "ms_upload": info.ms_upload},
+                        "node_tests_per_ray": n_node, "tri_tests_per_ray": n_tri, "wall_s_timed_region": t_wall},
             "gpu_launches": args.steps * launches_per_step * world,
             "clocks": clocks,
+            "parity": parity,
             "e2e": e2e,
             "stages_ms": {k: float(v) for k, v in zip(_lib.RTB_STAGES, stage_ms)},
-            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "fp32_issue", "kernel": dom_kernel, "achieved": ops_launch / launch_s / 1e12,
+                         "peak": fp32_peak / 1e12, "unit": "Tlane-op/s", "frac": ops_launch / launch_s / fp32_peak,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": f"{N_SM} SMs x {FP32_LANES_PER_SM} FP32 lanes x {sm_max_mhz:.0f} MHz (non-FMA: the exactness contract forbids contraction; SURVEY 8d)",
                          "launch_ms": float(stage_ms[3]), "share_of_step": float(stage_ms[3] / max(stage_ms.sum(), 1e-9)),
-                         "algorithmic_bytes_per_launch": bytes_launch,
+                         "algorithmic_lane_ops_per_launch": ops_launch,
+                         "lane_ops_per_ray": nb_node * 24 + nb_tri * 54 + 45,
                          "per_ray": {"aabb_tests": nb_node, "tri_tests": nb_tri, "rays": b_rays},
-                         "note": "algorithmic bytes = rays*(32*N_aabb + 80*N_tri + 16) are served by L1/L2 (the scene is "
-                                 "cache resident; measured DRAM traffic is `traffic`), so `frac` can exceed 1 and the "
-                                 "kernel's real bound is FP32/ALU issue under divergence: see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32_issue", "kernel": dom_kernel, "achieved": ops_launch / bounce_s / 1e12,
-                              "peak": fp32_peak / 1e12, "unit": "Tlane-op/s", "frac": ops_launch / bounce_s / fp32_peak,
-                              "whole_step_frac": step_ops / (ms_mine * 1e-3) / fp32_peak,
-                              "lane_ops_per_ray": nb_node * 24 + nb_tri * 54 + 45},
+                         "whole_step_frac": step_ops / (ms_mine * 1e-3) / fp32_peak},
+            "roofline_hbm": {"bound": "hbm", "kernel": dom_kernel, "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": bytes_launch,
+                             "algorithmic_gbs": bytes_launch / launch_s / 1e9,
+                             "measured_dram_bytes_per_launch": traffic, "measured_source": traffic_src,
+                             "achieved": (traffic / launch_s / 1e9) if traffic else None,
+                             "frac": (traffic / launch_s / 1e9 / hbm_peak) if traffic else None,
+                             "note": "the scene is cache resident: algorithmic bytes are served by L1/L2, DRAM sees the "
+                                     "workspace streaming through; HBM is not the bound of this path (SURVEY 8d)"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
+        if parity is not None:
+            bad = [k for k in ("equals_golden", "equals_n1", "rays_equal_n1", "e2e_equals_device_frame") if parity.get(k) is False]
+            if bad:
+                print(f"bench.py: PARITY FAILURE: {bad}", file=sys.stderr, flush=True)
+                ok = False
+    if shared_frame and rank != 0:
+        L.rtb_ipc_close(0, frame_ptr)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 def main():

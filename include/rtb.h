@@ -95,6 +95,12 @@ enum {
                                  launching stream and report RtbStats.ms_stage (one piece, one lane)  */
     RTB_FLAG_RESERVED32 = 32u, /* was RTB_FLAG_POOL (round 1's shared-memory ray-pool bounce kernel, measured slower and
                                  removed); ignored                                   */
+    RTB_FLAG_BVH8     = 128u, /* A/B: traverse the 8-wide compressed BVH (80-byte nodes, 8-bit child boxes, octant-ordered hit
+                                 masks) instead of the 4-wide uncompressed one; same results, measured 35 % slower on
+                                 cache-resident scenes.  The scene must have been created with
+                                 RTB_BVH8=1 in the environment, else RTB_ERR_INVALID                                */
+    RTB_FLAG_COPY_ONLY = 256u, /* measurement: rtb_render / rtb_render_rgb8 issue every copy and event of the frame but launch no
+                                 kernel — the device-to-host floor of the call (bench.py `e2e.d2h_floor_ms`)          */
     RTB_FLAG_FUSED    = 64u   /* A/B: primary phase and bounce phase of the path kernel as ONE launch per sample (the bounce
                                  phase consumes the queue while the primary phase still fills it) instead of two; same
                                  results, measured 5 % slower on one GPU and equal on a 1/8 share      */
@@ -257,6 +263,19 @@ int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t*
 /* Device self-test of the BVH builder's hand-written radix sort (stable, 64-bit keys, 32-bit values) and exclusive
  * scans against the host on n pseudo-random pairs with key_bits significant key bits. */
 int rtb_selftest_sort(uint32_t n, int key_bits, uint64_t seed);
+
+/* ---- one process per GPU, one frame on one GPU (torchrun; reference: the row queue all workers write one `data` slice
+ * from, raytrace.rs:1179-1194) ------------------------------------------------------------------------------------
+ * The root rank allocates the frame with rtb_device_alloc and exports it (rtb_ipc_export, a 64-byte
+ * cudaIpcMemHandle_t to be sent to the other ranks by any means); every other rank maps it with rtb_ipc_open and passes
+ * the mapped pointer to rtb_render_device as d_rgba: its kernels then store their bands straight into the root GPU's
+ * memory over NVLink peer access, and the frame is complete on the root GPU as soon as every rank's stream has drained —
+ * no gather kernel, no copy, no collective. */
+int rtb_device_alloc(int gpu, size_t bytes, void** d_ptr);           /* zero-filled device memory on GPU slot `gpu` */
+int rtb_device_free(int gpu, void* d_ptr);
+int rtb_ipc_export(void* d_ptr, unsigned char handle_out[64]);
+int rtb_ipc_open(int gpu, const unsigned char handle[64], void** d_ptr_out);
+int rtb_ipc_close(int gpu, void* d_ptr);
 
 /* Pin / unpin a caller-owned host buffer (cudaHostRegister) so D2H runs at PCIe speed. */
 int rtb_host_register(void* ptr, size_t bytes);

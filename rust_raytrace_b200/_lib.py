@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("RTB_LIB", os.path.join(_PKG, "librtb.so"))   # RTB_LI
 
 RTB_OK, RTB_ERR_NO_DEVICE, RTB_ERR_CUDA, RTB_ERR_INVALID, RTB_ERR_NOMEM = 0, -1, -2, -3, -4
 RTB_SOLID, RTB_MATTE, RTB_REFLECTIVE = 0, 1, 2
-RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL, RTB_FLAG_TIMING, RTB_FLAG_FUSED = 1, 2, 4, 8, 16, 64
+RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL, RTB_FLAG_TIMING, RTB_FLAG_FUSED, RTB_FLAG_BVH8, RTB_FLAG_COPY_ONLY = 1, 2, 4, 8, 16, 64, 128, 256
 RTB_STAGES = ("raygen", "trace", "shade", "bounce")
 RTB_MAX_DEPTH = 16
 
@@ -113,6 +113,7 @@ RTB_SYMBOLS = [
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render_rgb8", "rtb_scene_create_instanced", "rtb_assemble_triangles",
     "rtb_cull_triangles", "rtb_scene_create_ext", "rtb_scene_set_light", "rtb_render", "rtb_render_device", "rtb_render_progressive",
     "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
+    "rtb_device_alloc", "rtb_device_free", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close",
 ]
 RTBH_SYMBOLS = [
     "rtbh_make_color", "rtbh_unit", "rtbh_to_radians", "rtbh_make_triangle", "rtbh_make_dummy_triangle",
@@ -167,6 +168,11 @@ def lib():
     L.rtb_partition_rows.argtypes = [u32, u32, u32, vp, u32]
     L.rtb_host_register.argtypes = [vp, C.c_size_t]
     L.rtb_host_unregister.argtypes = [vp]
+    L.rtb_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.rtb_device_free.argtypes = [C.c_int, vp]
+    L.rtb_ipc_export.argtypes = [vp, C.c_char_p]
+    L.rtb_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.rtb_ipc_close.argtypes = [C.c_int, vp]
     # host helpers
     S = C.POINTER(RtbSurface)
     L.rtbh_make_color.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, f]

@@ -99,6 +99,7 @@ void free_gpu_scene(GpuScene& g) {
     if (g.device < 0) return;
     cudaSetDevice(g.device);
     if (g.stream) cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_nodes8); cudaFree(g.d_tri8); cudaFree(g.d_shade8);
     cudaFree(g.d_nodes); cudaFree(g.d_nodes4); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
     cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t); cudaFree(g.d_rgb8);
     for (auto& l : g.lanes) {
@@ -163,6 +164,7 @@ SceneDev scene_dev(const GpuScene& g, uint32_t n_prims) {
     s.height = g.height;
     s.nodes4 = g.d_nodes4;
     s.stack4 = g.stack4_need ? g.stack4_need + 1u : 3u * (g.depth4 + 1u) + 2u;    // exact bound from the builder, else 3 per level
+    s.nodes8 = g.d_nodes8; s.tri8 = g.d_tri8; s.shade8 = g.d_shade8; s.depth8 = g.depth8;
     return s;
 }
 
@@ -269,7 +271,8 @@ int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d
         if (vd.my_tile_rows == 0) continue;
         const uint32_t l = c % n_lanes;
         cudaStream_t ls = l == 0 ? st : g.lanes[l].st;     // lane 0 is the caller's stream itself
-        int rc = launch_frame(g, g.lanes[l], n_prims, vd, d_rgba, d_prim, d_t, ls, launches, primary);
+        int rc = (whole.flags & RTB_FLAG_COPY_ONLY) ? (int)RTB_OK
+                                                    : launch_frame(g, g.lanes[l], n_prims, vd, d_rgba, d_prim, d_t, ls, launches, primary);
         if (rc != RTB_OK) return rc;
         rc = after_piece(c, vd, ls);
         if (rc != RTB_OK) return rc;
@@ -479,6 +482,7 @@ int scene_create_common(const TriSource& src, const float root_orig[3], float ro
         g.n_nodes = br.n_nodes;
         g.height = br.tree_height;
         g.d_nodes4 = br.d_nodes4; g.n_nodes4 = br.n_nodes4; g.depth4 = br.depth4; g.stack4_need = br.stack4_need;
+        g.d_nodes8 = br.d_nodes8; g.d_tri8 = br.d_tri8; g.d_shade8 = br.d_shade8; g.n_nodes8 = br.n_nodes8; g.depth8 = br.depth8;
         g.has_spheres = src.n_spheres > 0;
         if (rc != RTB_OK) return bail(rc);
         if (gi == 0) {
@@ -726,7 +730,7 @@ int render_host(rtb_scene* s, const RtbView* view, float* rgba_out, uint8_t* rgb
                            g.stream, pieces, n_lanes, &launches, &primary_total,
                            [&](uint32_t c, const ViewDev& vd, cudaStream_t ls) -> int {
             // the piece's bands go home on the copy stream as soon as its kernels are done
-            if (rgb8_out) {      // write_png's `(c * 255.) as u8` (raytrace.rs:1468-1473) on the piece's pixels, on its stream
+            if (rgb8_out && !(vd.flags & RTB_FLAG_COPY_ONLY)) {      // write_png's `(c * 255.) as u8` (raytrace.rs:1468-1473) on the piece's pixels, on its stream
                 const size_t first_px = (size_t)vd.band_begin * RTB_TILE_H * W, n_px = (size_t)vd.my_tile_rows * RTB_TILE_H * W;
                 int rcq = rtb_launch_quantize(g.d_rgba + first_px, n_px, g.d_rgb8 + 3 * first_px, ls);
                 if (rcq != RTB_OK) return rcq;
@@ -957,6 +961,55 @@ int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t*
         ++n;
     }
     return (int)n;
+}
+
+int rtb_device_alloc(int gpu, size_t bytes, void** d_ptr) {
+    if (!d_ptr) return fail(RTB_ERR_INVALID, "d_ptr is NULL");
+    *d_ptr = nullptr;
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    if (gpu < 0 || gpu >= (int)g_devices.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
+    RTB_CUDA(cudaSetDevice(g_devices[gpu]));
+    RTB_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 4));
+    RTB_CUDA(cudaMemset(*d_ptr, 0, bytes ? bytes : 4));
+    RTB_CUDA(cudaDeviceSynchronize());
+    return RTB_OK;
+}
+
+int rtb_device_free(int gpu, void* d_ptr) {
+    if (gpu < 0 || gpu >= (int)g_devices.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
+    RTB_CUDA(cudaSetDevice(g_devices[gpu]));
+    RTB_CUDA(cudaFree(d_ptr));
+    return RTB_OK;
+}
+
+int rtb_ipc_export(void* d_ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!d_ptr || !handle_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    RTB_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle_out, &h, 64);
+    return RTB_OK;
+}
+
+int rtb_ipc_open(int gpu, const unsigned char handle[64], void** d_ptr_out) {
+    if (!handle || !d_ptr_out) return fail(RTB_ERR_INVALID, "NULL argument");
+    *d_ptr_out = nullptr;
+    int rc = ensure_init();
+    if (rc != RTB_OK) return rc;
+    if (gpu < 0 || gpu >= (int)g_devices.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
+    RTB_CUDA(cudaSetDevice(g_devices[gpu]));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    RTB_CUDA(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTB_OK;
+}
+
+int rtb_ipc_close(int gpu, void* d_ptr) {
+    if (gpu < 0 || gpu >= (int)g_devices.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
+    RTB_CUDA(cudaSetDevice(g_devices[gpu]));
+    RTB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RTB_OK;
 }
 
 int rtb_host_register(void* ptr, size_t bytes) {

@@ -36,6 +36,11 @@ struct SceneDev {
     uint32_t height;     // tree height: the traversal stack never holds more than `height` entries
     const float4* nodes4;   // 4-wide collapse of the same tree: 8 x float4 (128 B) per node, see rtb_lbvh.cu
     uint32_t stack4;     // stack entries a BVH4 traversal can need: 3 per level
+    // 8-wide compressed collapse (80 B per node) with its own reference order: tri8 / shade8 are tri / shade permuted
+    const uint4* nodes8;
+    const float4* tri8;
+    const float4* shade8;
+    uint32_t depth8;     // levels of the BVH8: its traversal stack holds at most one entry per level
 };
 
 #define RTB_TRI_F4 5
@@ -126,6 +131,10 @@ struct GpuScene {
     uint32_t height = 0;
     float4* d_nodes4 = nullptr;
     uint32_t n_nodes4 = 0, depth4 = 0, stack4_need = 0;
+    uint4* d_nodes8 = nullptr;
+    float4* d_tri8 = nullptr;
+    float4* d_shade8 = nullptr;
+    uint32_t n_nodes8 = 0, depth8 = 0;
     GpuLane lanes[RTB_MAX_LANES];
     cudaEvent_t fork_ev = nullptr;
     // scenes with analytic spheres or a light are rendered by the extension renderer (rtb_ext.cu)
@@ -158,6 +167,10 @@ struct BuildResult {
     uint32_t n_refs = 0;             // primitive references in the tree (>= n_prims: long primitives are split)
     float4* d_nodes4 = nullptr;      // 4-wide collapse, 8 x float4 per node
     uint32_t n_nodes4 = 0, depth4 = 0, stack4_need = 0;   // stack4_need: exact BVH4 stack bound (0 = use 3 per level)
+    uint4* d_nodes8 = nullptr;       // 8-wide compressed collapse, 5 x uint4 per node, and the references in its order
+    float4* d_tri8 = nullptr;
+    float4* d_shade8 = nullptr;
+    uint32_t n_nodes8 = 0, depth8 = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     float ms_build = 0.f;
     uint32_t launches = 0;

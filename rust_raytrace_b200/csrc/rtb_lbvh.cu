@@ -14,6 +14,7 @@
 //   k_emit_nodes    32-byte BVH2 nodes with adjacent sibling pairs (one-kernel renderers, rtb_scene_download_bvh)
 //   k_emit_tris     gather the 19 intersect floats + shading record of each reference into leaf order
 //   k_cost4/k_mark4/k_emit_nodes4   4-wide collapse chosen by dynamic programming, 128-byte BVH4 nodes (wavefront renderer)
+//   k_c8_level/k_emit_tris8         8-wide compressed collapse, 80-byte nodes, one level per launch (A/B, only with RTB_BVH8=1)
 
 #include <algorithm>
 #include <cfloat>
@@ -964,6 +965,161 @@ __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const in
     out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ---- 8-wide compressed collapse (A/B accelerator of the wavefront renderer, RTB_BVH8=1 + RTB_FLAG_BVH8) ---------------------
+// An 80-byte node with up to eight children, after Ylitie, Karras & Laine, "Efficient Incoherent Ray Traversal on GPUs
+// Through Compressed Wide BVHs" (HPG 2017), built from the same binary tree (blo/bhi already refitted):
+//   n0  p.x p.y p.z            origin of the node's quantisation frame (= lower corner of the padded node box)
+//       ex | ey<<8 | ez<<16 | imask<<24     per-axis scale 2^(e-127) (biased exponent bytes); imask: slots that hold child NODES
+//   n1  child_base  tri_base  meta[0..3]  meta[4..7]
+//         meta: 0 = empty slot; child node: 0b001_11sss (low 5 bits = 24 + slot); leaf: unary count (1, 3, 7) << 5 | offset
+//         of its first reference relative to tri_base (a node's leaf slots hold <= 24 references, contiguous in `tri8`)
+//   n2..n4  qlo_x[8] qlo_y[8] qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]   child boxes, 8 bits per plane: p + q * 2^(e-127),
+//         lower planes rounded down, upper planes rounded up (of the box padded like the BVH2 / BVH4 boxes)
+// Child nodes of one node are contiguous (child_base + rank among the node's internal slots), so a traversal stack entry
+// is (child_base, hit bits | imask) — 8 bytes for up to eight children — and slots are ASSIGNED by octant (the child in
+// the (-,-,-) corner of the node goes to slot 0, ...) so that `slot ^ ray octant` orders the hits front to back with no sort.
+// Which descendants become the eight children: start from the two BVH2 children, keep opening the entry with the largest
+// surface area among those covering more than 3 references; then, while slots are free, open the largest 2- or 3-reference
+// entries too — an empty slot costs the same eight box tests, a single-reference slot is that reference's own (quantised)
+// bounding box, so most exact triangle tests are preceded by a box test of the triangle itself.
+struct C8Item { int node; uint32_t out; };
+struct C8State { uint32_t n_next, n_nodes, n_tris, depth; };
+
+__device__ __forceinline__ int c8_size(int c, int n, const int2* __restrict__ range) {
+    return c >= n - 1 ? 1 : range[c].y - range[c].x + 1;
+}
+
+__global__ void k_c8_level(const C8Item* __restrict__ items, uint32_t n_items, C8Item* __restrict__ next, C8State* st,
+                           int n, const int2* __restrict__ children, const int2* __restrict__ range,
+                           const float4* __restrict__ blo, const float4* __restrict__ bhi, const BuildScratch* __restrict__ s,
+                           uint4* __restrict__ nodes8, uint32_t* __restrict__ perm8, uint32_t level) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const C8Item it = items[i];
+    const float pad = o2f(s->max_abs) * (1.0f / 131072.0f);   // 2^-17 of the largest |coordinate|, as for the other node arrays
+    int ent[8];
+    int cnt = 0;
+    if (it.node < 0) {                 // tiny scene without an internal BVH2 node: the single Karras leaf
+        ent[cnt++] = n - 1;
+    } else {
+        const int2 ch = children[it.node];
+        ent[cnt++] = ch.x; ent[cnt++] = ch.y;
+    }
+    // open entries: first the big ones (they cannot be leaf slots), then 2-3 reference groups while slots are free
+    for (int pass = 0; pass < 2; ++pass) {
+        while (cnt < 8) {
+            int best = -1; float best_a = -1.f;
+            for (int k = 0; k < cnt; ++k) {
+                const int sz = c8_size(ent[k], n, range);
+                if (pass == 0 ? sz <= 3 : sz < 2) continue;
+                const float a = box_area(blo[ent[k]], bhi[ent[k]]);
+                if (a > best_a) { best_a = a; best = k; }
+            }
+            if (best < 0) break;
+            const int2 ch = children[ent[best]];
+            ent[best] = ch.x; ent[cnt++] = ch.y;
+        }
+    }
+    // node frame
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float4 el[8], eh[8];
+    for (int k = 0; k < cnt; ++k) {
+        el[k] = blo[ent[k]]; eh[k] = bhi[ent[k]];
+        el[k].x -= pad; el[k].y -= pad; el[k].z -= pad; eh[k].x += pad; eh[k].y += pad; eh[k].z += pad;
+        lo[0] = fminf(lo[0], el[k].x); lo[1] = fminf(lo[1], el[k].y); lo[2] = fminf(lo[2], el[k].z);
+        hi[0] = fmaxf(hi[0], eh[k].x); hi[1] = fmaxf(hi[1], eh[k].y); hi[2] = fmaxf(hi[2], eh[k].z);
+    }
+    uint32_t eb[3];
+    float inv_scale[3];
+    for (int a = 0; a < 3; ++a) {
+        // smallest power of two with 254 * scale >= extent (254, not 255: headroom for the rounded-up subtraction below)
+        const float t = __fdiv_ru(__fsub_ru(hi[a], lo[a]), 254.0f);
+        uint32_t bits = __float_as_uint(t);
+        uint32_t e = bits >> 23;                                   // t >= 0
+        if (bits & 0x007fffffu) ++e;
+        e = min(max(e, 1u), 254u);
+        eb[a] = e;
+        inv_scale[a] = __uint_as_float((254u - e) << 23);         // 2^(127-e), exact
+    }
+    // octant slot assignment: greedily give (child, slot) pairs with the best alignment of the child's offset from the
+    // node centre with the slot's corner direction
+    const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+    int slot_of[8], child_in[8];
+    for (int k = 0; k < 8; ++k) { slot_of[k] = -1; child_in[k] = -1; }
+    for (int round = 0; round < cnt; ++round) {
+        float bestv = -FLT_MAX; int bk = -1, bs = -1;
+        for (int k = 0; k < cnt; ++k) {
+            if (slot_of[k] >= 0) continue;
+            const float dx = 0.5f * (el[k].x + eh[k].x) - cx, dy = 0.5f * (el[k].y + eh[k].y) - cy, dz = 0.5f * (el[k].z + eh[k].z) - cz;
+            for (int sl = 0; sl < 8; ++sl) {
+                if (child_in[sl] >= 0) continue;
+                const float v = ((sl & 1) ? dx : -dx) + ((sl & 2) ? dy : -dy) + ((sl & 4) ? dz : -dz);
+                if (v > bestv) { bestv = v; bk = k; bs = sl; }
+            }
+        }
+        slot_of[bk] = bs; child_in[bs] = bk;
+    }
+    // children: nodes (more than 3 references) get consecutive indices in slot order, leaf slots consecutive references
+    uint32_t n_int = 0, n_tri = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        if (child_in[sl] < 0) continue;
+        const int sz = c8_size(ent[child_in[sl]], n, range);
+        if (sz > 3) ++n_int; else n_tri += (uint32_t)sz;
+    }
+    const uint32_t child_base = n_int ? atomicAdd(&st->n_nodes, n_int) : 0u;
+    const uint32_t item_base = n_int ? atomicAdd(&st->n_next, n_int) : 0u;
+    const uint32_t tri_base = n_tri ? atomicAdd(&st->n_tris, n_tri) : 0u;
+    uint32_t meta[8], qlo[3][8], qhi[3][8];
+    uint32_t imask = 0, ri = 0, rt = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        meta[sl] = 0u;
+        for (int a = 0; a < 3; ++a) { qlo[a][sl] = 0u; qhi[a][sl] = 0u; }
+        const int k = child_in[sl];
+        if (k < 0) continue;
+        const int c = ent[k];
+        const int sz = c8_size(c, n, range);
+        if (sz > 3) {
+            imask |= 1u << sl;
+            meta[sl] = (1u << 5) | (24u + (uint32_t)sl);
+            next[item_base + ri].node = c; next[item_base + ri].out = child_base + ri;
+            ++ri;
+        } else {
+            meta[sl] = (((1u << sz) - 1u) << 5) | rt;
+            const int first = c >= n - 1 ? c - (n - 1) : range[c].x;
+            for (int j = 0; j < sz; ++j) perm8[tri_base + rt + j] = (uint32_t)(first + j);
+            rt += (uint32_t)sz;
+        }
+        const float l3[3] = {el[k].x, el[k].y, el[k].z}, h3[3] = {eh[k].x, eh[k].y, eh[k].z};
+        for (int a = 0; a < 3; ++a) {
+            // p + q * scale <= lower plane, p + q * scale >= upper plane (the division by a power of two is exact)
+            const float ql = floorf(__fsub_rd(l3[a], lo[a]) * inv_scale[a]);
+            const float qh = ceilf(__fsub_ru(h3[a], lo[a]) * inv_scale[a]);
+            qlo[a][sl] = (uint32_t)fminf(fmaxf(ql, 0.0f), 255.0f);
+            qhi[a][sl] = (uint32_t)fminf(fmaxf(qh, 0.0f), 255.0f);
+        }
+    }
+    auto pack4 = [](const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    uint4* out = nodes8 + 5u * (size_t)it.out;
+    out[0] = make_uint4(__float_as_uint(lo[0]), __float_as_uint(lo[1]), __float_as_uint(lo[2]),
+                        eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+    out[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+    out[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    out[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    out[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    if (i == 0) atomicMax(&st->depth, level);
+}
+
+// references gathered into BVH8 order: position i holds leaf-order reference perm8[i]
+__global__ void k_emit_tris8(const float4* __restrict__ tri, const float4* __restrict__ shade,
+                             const uint32_t* __restrict__ perm8, uint32_t n, float4* __restrict__ tri8,
+                             float4* __restrict__ shade8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = perm8[i];
+    for (int j = 0; j < RTB_TRI_F4; ++j) tri8[(size_t)RTB_TRI_F4 * i + j] = tri[(size_t)RTB_TRI_F4 * k + j];
+    for (int j = 0; j < RTB_SHADE_F4; ++j) shade8[(size_t)RTB_SHADE_F4 * i + j] = shade[(size_t)RTB_SHADE_F4 * k + j];
+}
+
 __global__ void k_emit_tris(const RtbTriangle* __restrict__ tris, const uint32_t* __restrict__ keep,
                             const uint32_t* __restrict__ sorted_vals, uint32_t n, float4* __restrict__ tri,
                             float4* __restrict__ shade, uint32_t* __restrict__ prim_order) {
@@ -1000,6 +1156,7 @@ inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 static void free_result(BuildResult* r) {
     cudaFree(r->d_nodes); cudaFree(r->d_nodes4); cudaFree(r->d_tri); cudaFree(r->d_shade); cudaFree(r->d_prim_order);
+    cudaFree(r->d_nodes8); cudaFree(r->d_tri8); cudaFree(r->d_shade8);
     *r = BuildResult();
 }
 
@@ -1122,6 +1279,12 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
         RTB_CUDA(cudaMemcpyAsync(out->d_nodes4, h4, sizeof h4, cudaMemcpyHostToDevice, stream));
         RTB_CUDA(cudaStreamSynchronize(stream));
         out->n_nodes4 = 1;
+        RTB_CUDA(cudaMalloc(&out->d_nodes8, sizeof(uint4) * 5));
+        RTB_CUDA(cudaMemsetAsync(out->d_nodes8, 0, sizeof(uint4) * 5, stream));       // every meta byte 0: eight empty slots
+        RTB_CUDA(cudaMalloc(&out->d_tri8, sizeof(float4) * RTB_TRI_F4));
+        RTB_CUDA(cudaMalloc(&out->d_shade8, sizeof(float4) * RTB_SHADE_F4));
+        RTB_CUDA(cudaStreamSynchronize(stream));
+        out->n_nodes8 = 1; out->depth8 = 0;
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(s0); cudaEventDestroy(s1); cudaEventDestroy(s2); cudaEventDestroy(s3);
         return RTB_OK;
     }
@@ -1303,6 +1466,44 @@ static int build_impl(const RtbTriangle* d_tris, const uint32_t* d_keep, uint32_
     RTB_CUDA(cudaMalloc(&out->d_nodes4, sizeof(float4) * 8 * (size_t)total4));
     k_emit_nodes4<<<cdiv(n_int > 0 ? n_int : 1, B), B, 0, stream>>>((int)n, children.p, range.p, blo.p, bhi.p, flags4.p,
                                                                   idx4.p, kind.p, out->d_nodes4, scratch.p, collapse_dp ? cut4.p : nullptr); ++launches;
+    // 8-wide compressed collapse of the same tree, one launch per BVH8 level.  Measured slower than the BVH4 on this path
+    // (cache-resident scenes: the decode costs more issue slots than the compression saves), so it is
+    // built only on request: RTB_BVH8=1 in the environment when the scene is created (read per call), used with RTB_FLAG_BVH8.
+    const char* want8 = getenv("RTB_BVH8");
+    if (want8 && atoi(want8) != 0) {
+        DevBuf<C8Item> it_a, it_b;
+        DevBuf<C8State> c8st;
+        DevBuf<uint4> nodes8_tmp;
+        DevBuf<uint32_t> perm8;
+        const uint32_t max_nodes8 = n_int + 1, max_items = n / 4 + 8;      // a child node covers > 3 references of its own
+        RTB_CUDA(it_a.alloc(max_items)); RTB_CUDA(it_b.alloc(max_items)); RTB_CUDA(c8st.alloc(1));
+        RTB_CUDA(nodes8_tmp.alloc(5 * (size_t)max_nodes8)); RTB_CUDA(perm8.alloc(n));
+        C8Item root; root.node = n_int > 0 ? 0 : -1; root.out = 0;
+        C8State hs8; hs8.n_next = 0; hs8.n_nodes = 1; hs8.n_tris = 0; hs8.depth = 0;
+        RTB_CUDA(cudaMemcpyAsync(it_a.p, &root, sizeof root, cudaMemcpyHostToDevice, stream));
+        RTB_CUDA(cudaMemcpyAsync(c8st.p, &hs8, sizeof hs8, cudaMemcpyHostToDevice, stream));
+        C8Item* cur = it_a.p; C8Item* nxt = it_b.p;
+        uint32_t n_items = 1, level = 0;
+        while (n_items > 0) {
+            k_c8_level<<<cdiv(n_items, 64), 64, 0, stream>>>(cur, n_items, nxt, c8st.p, (int)n, children.p, range.p, blo.p, bhi.p,
+                                                           scratch.p, nodes8_tmp.p, perm8.p, level); ++launches;
+            RTB_CUDA(cudaMemcpyAsync(&hs8, c8st.p, sizeof hs8, cudaMemcpyDeviceToHost, stream));
+            RTB_CUDA(cudaStreamSynchronize(stream));
+            n_items = hs8.n_next;
+            if (n_items > max_items) { rtb_set_error("BVH8 collapse: work list overflow"); return RTB_ERR_CUDA; }
+            RTB_CUDA(cudaMemsetAsync(&c8st.p->n_next, 0, sizeof(uint32_t), stream));
+            std::swap(cur, nxt);
+            ++level;
+        }
+        if (hs8.n_tris != n || hs8.n_nodes > max_nodes8) { rtb_set_error("BVH8 collapse: inconsistent counts"); return RTB_ERR_CUDA; }
+        out->n_nodes8 = hs8.n_nodes; out->depth8 = level;
+        RTB_CUDA(cudaMalloc(&out->d_nodes8, sizeof(uint4) * 5 * (size_t)hs8.n_nodes));
+        RTB_CUDA(cudaMemcpyAsync(out->d_nodes8, nodes8_tmp.p, sizeof(uint4) * 5 * (size_t)hs8.n_nodes, cudaMemcpyDeviceToDevice, stream));
+        RTB_CUDA(cudaMalloc(&out->d_tri8, sizeof(float4) * RTB_TRI_F4 * (size_t)n));
+        RTB_CUDA(cudaMalloc(&out->d_shade8, sizeof(float4) * RTB_SHADE_F4 * (size_t)n));
+        k_emit_tris8<<<cdiv(n, B), B, 0, stream>>>(out->d_tri, out->d_shade, perm8.p, n, out->d_tri8, out->d_shade8); ++launches;
+        RTB_CUDA(cudaStreamSynchronize(stream));      // the scratch buffers of this scope are freed stream-ordered
+    }
     RTB_CUDA(cudaEventRecord(e1, stream));
     BuildScratch h;
     RTB_CUDA(cudaMemcpyAsync(&h, scratch.p, sizeof h, cudaMemcpyDeviceToHost, stream));

@@ -173,6 +173,32 @@ def test_fused_launch_equals_the_two_phase_launches(R, O, scenes, spp, maxdepth,
     assert_bit_exact(b, bvh.render(O.main_viewport(*wh, maxdepth, spp), seed=23), f"fused {wh} spp={spp} maxdepth={maxdepth}")
 
 
+@pytest.mark.parametrize("det,spp,maxdepth,wh", [(False, 1, 5, (1283, 721)), (True, 1, 5, (640, 363)), (False, 3, 16, (333, 217))])
+def test_bvh8_equals_bvh4(R, O, det, spp, maxdepth, wh, monkeypatch):
+    """A/B accelerator: the 8-wide compressed BVH (80-byte nodes, quantised child boxes, octant-ordered hit masks, built
+    only with RTB_BVH8=1) against the default 4-wide uncompressed BVH of the same binary tree.  The closest hit does not
+    depend on the accelerator: ids, t, colour and ray count identical, both equal to the oracle."""
+    from rust_raytrace_b200 import _lib
+    monkeypatch.setenv("RTB_BVH8", "1")
+    s = R.main_scene(deterministic=det)
+    s.upload()
+    monkeypatch.delenv("RTB_BVH8")
+    v = R.main_viewport(*wh, maxdepth, spp)
+    a = gpu_render(R, s, v, seed=29, stats=True)
+    v8 = _lib.RtbView.from_buffer_copy(v)
+    v8.flags |= _lib.RTB_FLAG_BVH8
+    b = gpu_render(R, s, v8, seed=29, stats=True)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+    assert a[3].total_rays == b[3].total_rays
+    assert b[4].stats.node_tests != a[4].stats.node_tests          # it really was another tree
+    want = O.Scene(s.tris.view(O.TRI_DTYPE), O.ACCEL_BVH).render(O.main_viewport(*wh, maxdepth, spp), seed=29)
+    assert_bit_exact(a, want, f"bvh4 {wh}")
+    assert_bit_exact(b, want, f"bvh8 {wh}")
+    s.release()
+    with pytest.raises(_lib.RtbError):                               # a scene built without it refuses the flag
+        gpu_render(R, R.main_scene(deterministic=det), v8, seed=29)
+
+
 def test_fused_kernel_is_repeatable(R, scenes):
     """Twenty frames through the fused launch on one scene handle (the queue is never cleared: every launch has its own
     entry tag) — every frame identical, and identical again after a differently sized frame reused the workspace."""
