@@ -474,7 +474,7 @@ def run_gpu(args):
         if parity is not None and not by_samples:
             parity["e2e_equals_device_frame"] = bool(np.array_equal(data.view(np.uint32), frame_host.view(np.uint32)))
         if by_samples:
-            e2e["ms_reduce"] = float(getattr(caster.stats, "ms_stage")[2])     # rtb_render_progressive: reduce + D2H phase
+            e2e["ms_reduce"] = float(caster.stats.ms_reduce)     # rtb_render_progressive: cross-GPU reduce + copy home, max over GPUs
         if not by_samples:
             # the device-to-host floor of the same call: every copy and event of the frame, no kernel (RTB_FLAG_COPY_ONLY)
             vc = _lib.RtbView.from_buffer_copy(vv)

@@ -123,6 +123,7 @@ typedef struct RtbStats {
     uint64_t node_tests_bounce;  /* the share of node_tests / tri_tests spent in the bounce kernel        */
     uint64_t tri_tests_bounce;   /*   (RTB_FLAG_STATS only)                                               */
     double   ms_stage[4];        /* RTB_FLAG_TIMING: device ms per stage, summed over samples (CUDA events) */
+    double   ms_reduce;          /* rtb_render_progressive: device ms of the cross-GPU reduce + copy home, max over GPUs */
 } RtbStats;
 
 typedef struct RtbSceneInfo {
@@ -149,6 +150,7 @@ typedef struct rtb_scene rtb_scene;
  * set is allowed when no scene is alive. */
 int rtb_init(int n_gpus, const int* device_ids);
 int rtb_device_count(void);          /* devices selected by rtb_init, or <0 */
+int rtb_visible_device_count(void);  /* CUDA devices this process can see (no selection is changed), or RTB_ERR_NO_DEVICE */
 void rtb_shutdown(void);
 const char* rtb_last_error(void);
 

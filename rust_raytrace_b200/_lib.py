@@ -19,6 +19,7 @@ RTB_SOLID, RTB_MATTE, RTB_REFLECTIVE = 0, 1, 2
 RTB_FLAG_SUM_ONLY, RTB_FLAG_STATS, RTB_FLAG_BRUTE, RTB_FLAG_MEGAKERNEL, RTB_FLAG_TIMING, RTB_FLAG_FUSED, RTB_FLAG_BVH8, RTB_FLAG_COPY_ONLY = 1, 2, 4, 8, 16, 64, 128, 256
 RTB_STAGES = ("raygen", "trace", "shade", "bounce")
 RTB_MAX_DEPTH = 16
+RTB_MAX_GPUS = 8
 
 # numpy mirror of RtbTriangle (35 x 4 bytes; reference field order raytrace.rs:326-337)
 TRI_DTYPE = np.dtype(
@@ -70,6 +71,7 @@ class RtbStats(C.Structure):
         ("node_tests_bounce", C.c_uint64),
         ("tri_tests_bounce", C.c_uint64),
         ("ms_stage", C.c_double * 4),
+        ("ms_reduce", C.c_double),
     ]
 
 
@@ -109,7 +111,7 @@ class RtbMeshInstance(C.Structure):
 
 # Every symbol include/rtb.h and include/rtb_host.h declare (checked by tests/test_host.py::test_library_exports_every_declared_symbol).
 RTB_SYMBOLS = [
-    "rtb_init", "rtb_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
+    "rtb_init", "rtb_device_count", "rtb_visible_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render_rgb8", "rtb_scene_create_instanced", "rtb_assemble_triangles",
     "rtb_cull_triangles", "rtb_scene_create_ext", "rtb_scene_set_light", "rtb_render", "rtb_render_device", "rtb_render_progressive",
     "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
@@ -147,6 +149,7 @@ def lib():
     u32 = C.c_uint32
     L.rtb_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.rtb_device_count.argtypes = []
+    L.rtb_visible_device_count.argtypes = []
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_scene_create.argtypes = [vp, u32, f, C.c_float, C.POINTER(vp)]
     L.rtb_scene_create_instanced.argtypes = [vp, u32, vp, u32, vp, u32, vp, u32, f, C.c_float, C.POINTER(vp)]

@@ -2,6 +2,7 @@
 // frame rendering into host or device buffers, progressive multi-GPU rendering.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
@@ -18,6 +19,7 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 std::vector<int> g_devices;   // devices selected by rtb_init
+bool g_p2p[RTB_MAX_GPUS][RTB_MAX_GPUS] = {};   // [a][b]: GPU slot a can load from / store to GPU slot b's memory (rtb_init)
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -102,8 +104,13 @@ void free_gpu_scene(GpuScene& g) {
     cudaFree(g.d_nodes8); cudaFree(g.d_tri8); cudaFree(g.d_shade8);
     cudaFree(g.d_nodes); cudaFree(g.d_nodes4); cudaFree(g.d_tri); cudaFree(g.d_shade); cudaFree(g.d_prim_order); cudaFree(g.d_counters);
     cudaFree(g.d_rgba); cudaFree(g.d_prim); cudaFree(g.d_t); cudaFree(g.d_rgb8);
+    cudaFree(g.d_stage);
+    if (g.prog_done) cudaEventDestroy(g.prog_done);
+    if (g.red0) cudaEventDestroy(g.red0);
+    if (g.red1) cudaEventDestroy(g.red1);
     for (auto& l : g.lanes) {
         cudaFree(l.d_ws);
+        if (l.busy) cudaEventDestroy(l.busy);
         if (l.done) cudaEventDestroy(l.done);
         for (auto& e : l.stage_ev) if (e) cudaEventDestroy(e);
         if (l.st) cudaStreamDestroy(l.st);
@@ -138,6 +145,26 @@ int check_view(const RtbView* v) {
     if (v->spp == 0) return fail(RTB_ERR_INVALID, "samples_per_pixel must be >= 1");
     if (v->sample_end > v->spp || v->sample_begin > v->sample_end)
         return fail(RTB_ERR_INVALID, "sample range outside [0, spp]");
+    return RTB_OK;
+}
+
+// The conservative slab tests compute t = fma(plane, 1/d, -o/d): the rounding of o/d moves a plane by up to |o| * 2^-23,
+// which the builder's padding (2^-17 of the scene's largest |coordinate|) covers only while the ray origins stay within
+// 32x the scene's extent.  Bounce rays start on surfaces; primary rays start on the viewport plane — checked here.
+int check_camera(const rtb_scene* s, const RtbView* v) {
+    float max_abs = 0.f;
+    for (int k = 0; k < 3; ++k) max_abs = std::max(max_abs, std::max(std::fabs(s->info.scene_lo[k]), std::fabs(s->info.scene_hi[k])));
+    if (s->info.n_prims == 0 || !(max_abs > 0.f)) return RTB_OK;
+    float far = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        // the four corners of the viewport: orig, orig + vu, orig + vv, orig + vu + vv
+        const float c[4] = {v->orig[k], v->orig[k] + v->vu[k], v->orig[k] + v->vv[k], v->orig[k] + v->vu[k] + v->vv[k]};
+        for (float x : c) far = std::max(far, std::fabs(x));
+    }
+    if (!(far <= 32.0f * max_abs))
+        return fail(RTB_ERR_INVALID, "viewport farther from the origin than 32x the scene's largest coordinate (" + std::to_string(far) +
+                                         " vs " + std::to_string(max_abs) + "): beyond the range in which the BVH's box padding keeps the "
+                                         "traversal exact; move the camera closer or translate the scene (INTEGRATION.md, limits)");
     return RTB_OK;
 }
 
@@ -271,9 +298,16 @@ int render_pieces(GpuScene& g, uint32_t n_prims, const ViewDev& whole, float4* d
         if (vd.my_tile_rows == 0) continue;
         const uint32_t l = c % n_lanes;
         cudaStream_t ls = l == 0 ? st : g.lanes[l].st;     // lane 0 is the caller's stream itself
+        GpuLane& lane = g.lanes[l];
+        // the lane's workspace may still be in use by a frame issued earlier on ANOTHER stream (asynchronous
+        // rtb_render_device calls with different streams): that frame's kernels first
+        if (lane.used && lane.busy_stream != ls) RTB_CUDA(cudaStreamWaitEvent(ls, lane.busy, 0));
         int rc = (whole.flags & RTB_FLAG_COPY_ONLY) ? (int)RTB_OK
-                                                    : launch_frame(g, g.lanes[l], n_prims, vd, d_rgba, d_prim, d_t, ls, launches, primary);
+                                                    : launch_frame(g, lane, n_prims, vd, d_rgba, d_prim, d_t, ls, launches, primary);
         if (rc != RTB_OK) return rc;
+        if (!lane.busy) RTB_CUDA(cudaEventCreateWithFlags(&lane.busy, cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(lane.busy, ls));
+        lane.busy_stream = ls; lane.used = true;
         rc = after_piece(c, vd, ls);
         if (rc != RTB_OK) return rc;
     }
@@ -308,16 +342,19 @@ int rtb_init(int n_gpus, const int* device_ids) {
         if (d < 0 || d >= count) return fail(RTB_ERR_INVALID, "device id " + std::to_string(d) + " out of range");
         devs.push_back(d);
     }
-    // peer access between every pair (needed by rtb_render_progressive; harmless otherwise)
+    // peer access between every pair (rtb_render_progressive reads its peers' sample sums directly where it can and
+    // stages them with cudaMemcpyPeerAsync where it cannot); what works is recorded per pair
     for (size_t a = 0; a < devs.size(); ++a)
         for (size_t b = 0; b < devs.size(); ++b) {
+            g_p2p[a][b] = (a == b);
             if (a == b) continue;
             int can = 0;
-            cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
+            if (cudaDeviceCanAccessPeer(&can, devs[a], devs[b]) != cudaSuccess) { cudaGetLastError(); can = 0; }
             if (can) {
                 cudaSetDevice(devs[a]);
-                cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b], 0);
-                if (pe != cudaSuccess) cudaGetLastError();   // already enabled is fine
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[b], 0);
+                if (pe != cudaSuccess) cudaGetLastError();
+                g_p2p[a][b] = (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled);
             }
         }
     // scene-build scratch is stream-ordered (cudaMallocAsync): keep freed blocks in the pool instead of returning them
@@ -336,6 +373,16 @@ int rtb_init(int n_gpus, const int* device_ids) {
 }
 
 int rtb_device_count(void) { return g_devices.empty() ? RTB_ERR_INVALID : (int)g_devices.size(); }
+
+int rtb_visible_device_count(void) {
+    int count = 0;
+    const cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(RTB_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");
+    }
+    return count;
+}
 
 void rtb_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -631,6 +678,9 @@ int rtb_render_device(rtb_scene* s, const RtbView* view, int gpu, uint32_t tile_
     if (gpu < 0 || gpu >= (int)s->gpu.size()) return fail(RTB_ERR_INVALID, "gpu slot out of range");
     if (tile_world == 0 || tile_rank >= tile_world) return fail(RTB_ERR_INVALID, "bad tile_rank/tile_world");
     if (!d_rgba) return fail(RTB_ERR_INVALID, "d_rgba is NULL");
+    rc = check_camera(s, view);
+    if (rc != RTB_OK) return rc;
+    std::lock_guard<std::mutex> scene_lock(s->mu);
     GpuScene& g = s->gpu[gpu];
     RTB_CUDA(cudaSetDevice(g.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
@@ -681,6 +731,9 @@ int render_host(rtb_scene* s, const RtbView* view, float* rgba_out, uint8_t* rgb
     int rc = check_view(view);
     if (rc != RTB_OK) return rc;
     if (!rgba_out && !rgb8_out) return fail(RTB_ERR_INVALID, "output buffer is NULL");
+    rc = check_camera(s, view);
+    if (rc != RTB_OK) return rc;
+    std::lock_guard<std::mutex> scene_lock(s->mu);     // one frame at a time per handle: two threads may share a handle
     const double t0 = now_ms();
     const uint32_t world = (uint32_t)s->gpu.size();
     const uint32_t W = view->width, H = view->height;
@@ -833,23 +886,39 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
     int rc = check_view(view);
     if (rc != RTB_OK) return rc;
     if (!rgba_out) return fail(RTB_ERR_INVALID, "rgba_out is NULL");
+    rc = check_camera(s, view);
+    if (rc != RTB_OK) return rc;
+    std::lock_guard<std::mutex> scene_lock(s->mu);
     const double t0 = now_ms();
     const uint32_t world = (uint32_t)s->gpu.size();
     const uint32_t W = view->width, H = view->height;
     const size_t pixels = (size_t)W * H;
     const uint32_t s_lo = view->sample_begin, s_hi = (view->sample_begin == 0 && view->sample_end == 0) ? view->spp : view->sample_end;
     const uint32_t n_s = s_hi - s_lo;
-    uint32_t launches = 0;
-    uint64_t primary_total = 0;
+    const float inv_spp = 1.0f / (float)n_s;
+    std::vector<uint32_t> launches_r(world, 0);
+    std::vector<uint64_t> primary_r(world, 0);
+    std::vector<TraceCounters> cnt_r(world);
+    std::vector<float> ms_r(world, 0.f), msred_r(world, 0.f);
+    std::vector<std::string> err_r(world);
+    // direct peer loads only if EVERY pair can do them; else every peer's share is staged (one code path, not N^2)
+    bool all_p2p = true;
+    for (uint32_t a = 0; a < world; ++a)
+        for (uint32_t b = 0; b < world; ++b) all_p2p = all_p2p && g_p2p[a][b];
+    auto range_of = [&](uint32_t r, uint64_t* first, uint64_t* last) { *first = (uint64_t)pixels * r / world; *last = (uint64_t)pixels * (r + 1) / world; };
 
-    // phase 1: every GPU accumulates its contiguous share of the samples over the FULL frame (sum only)
-    std::vector<const float4*> bufs(world);
-    for (uint32_t r = 0; r < world; ++r) {
+    // phase 1 (per GPU, issue only): accumulate this GPU's contiguous share of the samples over the FULL frame (sum only),
+    // then record "my sums are complete"
+    auto phase1 = [&](uint32_t r) -> int {
         GpuScene& g = s->gpu[r];
         RTB_CUDA(cudaSetDevice(g.device));
-        rc = ensure_framebuffer(g, 2 * pixels, false, false);   // [0,pixels) = sum buffer, [pixels,2*pixels) = reduced band
+        int rc = ensure_framebuffer(g, 2 * pixels, false, false);   // [0,pixels) = sum buffer, [pixels,2*pixels) = reduced share
         if (rc != RTB_OK) return rc;
-        bufs[r] = g.d_rgba;
+        if (!g.prog_done) {
+            RTB_CUDA(cudaEventCreateWithFlags(&g.prog_done, cudaEventDisableTiming));
+            RTB_CUDA(cudaEventCreate(&g.red0));
+            RTB_CUDA(cudaEventCreate(&g.red1));
+        }
         RtbView v = *view;
         v.sample_begin = s_lo + (uint32_t)(((uint64_t)n_s * r) / world);
         v.sample_end = s_lo + (uint32_t)(((uint64_t)n_s * (r + 1)) / world);
@@ -859,58 +928,95 @@ int rtb_render_progressive(rtb_scene* s, const RtbView* view, float* rgba_out, R
         if (v.sample_begin == v.sample_end) {
             RTB_CUDA(cudaMemsetAsync(g.d_rgba, 0, pixels * sizeof(float4), g.stream));
         } else {
-            ViewDev vd = make_view(v, 0, 1, false);
-            uint64_t primary = 0;
-            rc = launch_frame(g, g.lanes[0], s->info.n_refs, vd, g.d_rgba, nullptr, nullptr, g.stream, &launches, &primary);
+            const ViewDev vd = make_view(v, 0, 1, false);
+            GpuLane& lane = g.lanes[0];
+            if (lane.used && lane.busy_stream != g.stream) RTB_CUDA(cudaStreamWaitEvent(g.stream, lane.busy, 0));
+            rc = launch_frame(g, lane, s->info.n_refs, vd, g.d_rgba, nullptr, nullptr, g.stream, &launches_r[r], &primary_r[r]);
             if (rc != RTB_OK) return rc;
-            primary_total += primary;
+            if (!lane.busy) RTB_CUDA(cudaEventCreateWithFlags(&lane.busy, cudaEventDisableTiming));
+            RTB_CUDA(cudaEventRecord(lane.busy, g.stream));
+            lane.busy_stream = g.stream; lane.used = true;
         }
         RTB_CUDA(cudaEventRecord(g.ev1, g.stream));
-    }
-    for (uint32_t r = 0; r < world; ++r) {
-        RTB_CUDA(cudaSetDevice(s->gpu[r].device));
-        RTB_CUDA(cudaStreamSynchronize(s->gpu[r].stream));
-    }
-    // phase 2: GPU r reduces pixel range r over NVLink peer loads, normalises and copies it home; all GPUs are issued
-    // first and waited for afterwards so that the eight reduces and the eight D2H copies (own PCIe links) overlap
-    const float inv_spp = 1.0f / (float)n_s;
-    std::vector<const float4**> d_ptrs(world, nullptr);
-    auto free_ptrs = [&]() { for (uint32_t r = 0; r < world; ++r) if (d_ptrs[r]) { cudaSetDevice(s->gpu[r].device); cudaFree(d_ptrs[r]); } };
-    for (uint32_t r = 0; r < world; ++r) {
+        RTB_CUDA(cudaEventRecord(g.prog_done, g.stream));
+        return RTB_OK;
+    };
+    // phase 2 (per GPU): wait on the device for every peer's sums (events, no host synchronisation), reduce pixel range r
+    // over NVLink peer loads fused with the 1/spp scale, copy the range home over this GPU's own PCIe link, read the counters
+    auto phase2 = [&](uint32_t r) -> int {
         GpuScene& g = s->gpu[r];
         RTB_CUDA(cudaSetDevice(g.device));
-        const uint64_t first = (uint64_t)pixels * r / world, last = (uint64_t)pixels * (r + 1) / world;
-        RTB_CUDA(cudaMalloc(&d_ptrs[r], sizeof(float4*) * world));
-        RTB_CUDA(cudaMemcpyAsync(d_ptrs[r], bufs.data(), sizeof(float4*) * world, cudaMemcpyHostToDevice, g.stream));
+        uint64_t first, last;
+        range_of(r, &first, &last);
+        for (uint32_t p = 0; p < world; ++p)
+            if (p != r) RTB_CUDA(cudaStreamWaitEvent(g.stream, s->gpu[p].prog_done, 0));
+        RTB_CUDA(cudaEventRecord(g.red0, g.stream));
+        RtbPeerBufs bufs;
+        for (uint32_t p = 0; p < RTB_MAX_GPUS; ++p) bufs.p[p] = p < world ? s->gpu[p].d_rgba : nullptr;
+        if (!all_p2p && world > 1) {
+            const size_t cnt = (size_t)(last - first);
+            if (g.stage_pixels < cnt * (world - 1)) {
+                RTB_CUDA(cudaStreamSynchronize(g.stream));
+                cudaFree(g.d_stage); g.d_stage = nullptr; g.stage_pixels = 0;
+                RTB_CUDA(cudaMalloc(&g.d_stage, cnt * (world - 1) * sizeof(float4)));
+                g.stage_pixels = cnt * (world - 1);
+            }
+            uint32_t k = 0;
+            for (uint32_t p = 0; p < world; ++p) {
+                if (p == r) continue;
+                float4* dst = g.d_stage + (size_t)k * cnt;
+                RTB_CUDA(cudaMemcpyPeerAsync(dst, g.device, s->gpu[p].d_rgba + first, s->gpu[p].device, cnt * sizeof(float4), g.stream));
+                bufs.p[p] = dst - first;          // indexed with [first + i] by the kernel
+                ++k;
+            }
+        }
         float4* d_out = g.d_rgba + pixels;
-        rc = rtb_launch_peer_reduce(d_ptrs[r], (int)world, inv_spp, first, last - first, d_out, g.stream);
-        ++launches;
-        if (rc != RTB_OK) { free_ptrs(); return rc; }
-        RTB_CUDA(cudaMemcpyAsync(rgba_out + 4 * first, d_out + first, (last - first) * sizeof(float4),
-                                 cudaMemcpyDeviceToHost, g.stream));
+        int rc = rtb_launch_peer_reduce(bufs, (int)world, inv_spp, first, last - first, d_out, g.stream);
+        if (rc != RTB_OK) return rc;
+        ++launches_r[r];
+        RTB_CUDA(cudaMemcpyAsync(rgba_out + 4 * first, d_out + first, (last - first) * sizeof(float4), cudaMemcpyDeviceToHost, g.stream));
+        RTB_CUDA(cudaEventRecord(g.red1, g.stream));
+        RTB_CUDA(cudaMemcpyAsync(&cnt_r[r], g.d_counters, sizeof(TraceCounters), cudaMemcpyDeviceToHost, g.stream));
+        RTB_CUDA(cudaStreamSynchronize(g.stream));
+        RTB_CUDA(cudaEventElapsedTime(&ms_r[r], g.ev0, g.ev1));
+        RTB_CUDA(cudaEventElapsedTime(&msred_r[r], g.red0, g.red1));
+        return RTB_OK;
+    };
+    // an event must be RECORDED before another stream is told to wait for it: all GPUs finish issuing phase 1 (a host-side
+    // join of the workers, nothing waits for the device) before any GPU issues phase 2
+    auto run_phase = [&](const std::function<int(uint32_t)>& fn) -> int {
+        if (world == 1) return fn(0);
+        std::vector<int> rcs(world, RTB_OK);
+        for (uint32_t r = 0; r < world; ++r)
+            g_workers[r]->start([&, r]() { rcs[r] = fn(r); if (rcs[r] != RTB_OK) err_r[r] = rtb_last_error(); });
+        for (uint32_t r = 0; r < world; ++r) g_workers[r]->wait();
+        for (uint32_t r = 0; r < world; ++r)
+            if (rcs[r] != RTB_OK) { g_err = err_r[r]; return rcs[r]; }
+        return RTB_OK;
+    };
+    {
+        std::unique_lock<std::mutex> lr(g_render_mu, std::defer_lock);
+        if (world > 1) { lr.lock(); ensure_workers(world); }
+        rc = run_phase(phase1);
+        if (rc == RTB_OK) rc = run_phase(phase2);
+        if (rc != RTB_OK) {      // leave no work in flight on an error path
+            for (uint32_t r = 0; r < world; ++r) { cudaSetDevice(s->gpu[r].device); cudaStreamSynchronize(s->gpu[r].stream); }
+            cudaGetLastError();
+            return rc;
+        }
     }
-    for (uint32_t r = 0; r < world; ++r) {
-        RTB_CUDA(cudaSetDevice(s->gpu[r].device));
-        RTB_CUDA(cudaStreamSynchronize(s->gpu[r].stream));
-    }
-    free_ptrs();
     RtbStats st;
     std::memset(&st, 0, sizeof st);
     for (uint32_t r = 0; r < world; ++r) {
-        GpuScene& g = s->gpu[r];
-        RTB_CUDA(cudaSetDevice(g.device));
-        TraceCounters c;
-        RTB_CUDA(cudaMemcpy(&c, g.d_counters, sizeof c, cudaMemcpyDeviceToHost));
-        float ms = 0.f;
-        RTB_CUDA(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        const TraceCounters& c = cnt_r[r];
         if (c.stalled) return fail(RTB_ERR_CUDA, "path kernel watchdog: a reserved bounce-queue entry never arrived");
-        st.rays += c.rays; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
+        st.rays += c.rays + primary_r[r]; st.node_tests += c.node_tests; st.tri_tests += c.tri_tests;
         st.bounce_rays += c.rays; st.node_tests_bounce += c.node_tests_bounce; st.tri_tests_bounce += c.tri_tests_bounce;
-        st.ms_render = std::max(st.ms_render, (double)ms);
+        st.ms_render = std::max(st.ms_render, (double)ms_r[r]);
+        st.ms_reduce = std::max(st.ms_reduce, (double)msred_r[r]);
+        st.kernel_launches += launches_r[r];
     }
-    st.rays += primary_total;
     st.ms_total = now_ms() - t0;
-    st.kernel_launches = launches;
     st.n_gpus = world;
     if (stats) *stats = st;
     return RTB_OK;
@@ -934,9 +1040,9 @@ int rtb_quantize_rgb8(const float* rgba, uint64_t npix, uint8_t* rgb_out) {
     uint8_t* d_out = nullptr;
     RTB_CUDA(cudaMalloc(&d_in, npix * sizeof(float4) + 16));
     if (cudaMalloc(&d_out, npix * 3 + 16) != cudaSuccess) { cudaFree(d_in); return fail(RTB_ERR_NOMEM, "cudaMalloc"); }
-    cudaMemcpy(d_in, rgba, npix * sizeof(float4), cudaMemcpyHostToDevice);
-    rc = rtb_launch_quantize(d_in, npix, d_out, 0);
-    cudaError_t e = cudaMemcpy(rgb_out, d_out, npix * 3, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(d_in, rgba, npix * sizeof(float4), cudaMemcpyHostToDevice);
+    rc = e == cudaSuccess ? rtb_launch_quantize(d_in, npix, d_out, 0) : rtb_cuda_fail(e, "cudaMemcpy(rgba)", __FILE__, __LINE__);
+    if (rc == RTB_OK) e = cudaMemcpy(rgb_out, d_out, npix * 3, cudaMemcpyDeviceToHost);
     cudaFree(d_in);
     cudaFree(d_out);
     if (rc != RTB_OK) return rc;

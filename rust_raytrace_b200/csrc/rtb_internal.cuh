@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -104,6 +105,9 @@ struct GpuLane {
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
     uint32_t epoch = 0;            // launches of the path kernel on this workspace (the bounce queue's entry tag)
+    cudaEvent_t busy = nullptr;    // recorded after the last kernel that used this workspace ...
+    cudaStream_t busy_stream = nullptr;   // ... on this stream: a frame issued on another stream waits for it first
+    bool used = false;
     cudaEvent_t stage_ev[RTB_N_STAGES + 1] = {};   // RTB_FLAG_TIMING: stage boundaries of one sample
     float stage_ms[RTB_N_STAGES] = {};
 };
@@ -137,6 +141,10 @@ struct GpuScene {
     uint32_t n_nodes8 = 0, depth8 = 0;
     GpuLane lanes[RTB_MAX_LANES];
     cudaEvent_t fork_ev = nullptr;
+    // rtb_render_progressive: "my sample sums are complete" (waited for by every peer's reduce), reduce timing, peer staging
+    cudaEvent_t prog_done = nullptr, red0 = nullptr, red1 = nullptr;
+    float4* d_stage = nullptr;
+    size_t stage_pixels = 0;
     // scenes with analytic spheres or a light are rendered by the extension renderer (rtb_ext.cu)
     bool has_spheres = false;
     ExtParams ext = {};
@@ -145,6 +153,7 @@ struct GpuScene {
 struct rtb_scene {
     std::vector<GpuScene> gpu;
     RtbSceneInfo info;
+    std::mutex mu;          // a handle serialises its render calls (workspaces, counters and frame buffers are per handle)
 };
 
 // ---- error plumbing ---------------------------------------------------------
@@ -210,7 +219,8 @@ int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace,
 
 int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream);
 int rtb_launch_scale(float4* d_rgba, uint64_t npix, float inv_spp, cudaStream_t stream);
-// Fused cross-GPU reduce of per-GPU sample sums over peer memory: out[i] = (sum_g bufs[g][i]) * inv_spp for
-// pixels [first, first+count).
-int rtb_launch_peer_reduce(const float4* const* d_bufs_on_device, int n_bufs, float inv_spp, uint64_t first,
+// Fused cross-GPU reduce of per-GPU sample sums over peer memory: out[i] = (sum_g bufs.p[g][i]) * inv_spp for
+// pixels [first, first+count).  The pointers travel by value (kernel parameters): no pointer table in device memory.
+struct RtbPeerBufs { const float4* p[RTB_MAX_GPUS]; };
+int rtb_launch_peer_reduce(const RtbPeerBufs& bufs, int n_bufs, float inv_spp, uint64_t first,
                            uint64_t count, float4* d_out, cudaStream_t stream);

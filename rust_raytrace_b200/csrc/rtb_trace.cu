@@ -211,30 +211,42 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
     }
 }
 
-// write_png's `(c*255.) as u8` (raytrace.rs:1468-1473): truncating, saturating, NaN -> 0
+// write_png's `(c*255.) as u8` (raytrace.rs:1468-1473): truncating, saturating, NaN -> 0.  One thread = four pixels =
+// three 32-bit stores (`rgb` is 4-byte aligned: every caller passes the start of a band or of an allocation).
+__device__ __forceinline__ uint32_t quant_u8(float c) {
+    const float v = __fmul_rn(c, 255.0f);
+    return v >= 255.0f ? 255u : (v > 0.0f ? (uint32_t)v : 0u);
+}
 __global__ void k_quantize(const float4* __restrict__ rgba, uint64_t npix, uint8_t* __restrict__ rgb) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    const float4 c = rgba[i];
-    const float v[3] = {__fmul_rn(c.x, 255.0f), __fmul_rn(c.y, 255.0f), __fmul_rn(c.z, 255.0f)};
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i0 >= npix) return;
+    if (i0 + 4u <= npix) {
+        uint32_t b[12];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        uint32_t q = 0;
-        if (v[k] >= 255.0f) q = 255u;
-        else if (v[k] > 0.0f) q = (uint32_t)v[k];
-        rgb[3 * i + k] = (uint8_t)q;
+        for (int k = 0; k < 4; ++k) {
+            const float4 c = __ldcs(rgba + i0 + k);
+            b[3 * k] = quant_u8(c.x); b[3 * k + 1] = quant_u8(c.y); b[3 * k + 2] = quant_u8(c.z);
+        }
+        uint32_t* out = reinterpret_cast<uint32_t*>(rgb + 3u * i0);
+#pragma unroll
+        for (int w = 0; w < 3; ++w) out[w] = b[4 * w] | (b[4 * w + 1] << 8) | (b[4 * w + 2] << 16) | (b[4 * w + 3] << 24);
+    } else {
+        for (uint64_t i = i0; i < npix; ++i) {
+            const float4 c = rgba[i];
+            rgb[3 * i] = (uint8_t)quant_u8(c.x); rgb[3 * i + 1] = (uint8_t)quant_u8(c.y); rgb[3 * i + 2] = (uint8_t)quant_u8(c.z);
+        }
     }
 }
 
 // Cross-GPU reduce over peer memory: every pointer in `bufs` may live on another GPU (NVLink P2P).
 // Sums in GPU-index order (deterministic), scales by 1/spp (walk_ray_set :1426).
-__global__ void k_peer_reduce(const float4* const* __restrict__ bufs, int n_bufs, float inv_spp, uint64_t first,
+__global__ void k_peer_reduce(const RtbPeerBufs bufs, int n_bufs, float inv_spp, uint64_t first,
                               uint64_t count, float4* __restrict__ out) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        float4 s = bufs[0][first + i];
+        float4 s = bufs.p[0][first + i];
         for (int g = 1; g < n_bufs; ++g) {
-            const float4 v = bufs[g][first + i];
+            const float4 v = bufs.p[g][first + i];
             s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z);
         }
         out[first + i] = make_float4(__fmul_rn(s.x, inv_spp), __fmul_rn(s.y, inv_spp), __fmul_rn(s.z, inv_spp), 0.0f);
@@ -273,15 +285,15 @@ int rtb_launch_scale(float4* d_rgba, uint64_t npix, float inv_spp, cudaStream_t 
 
 int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream) {
     if (npix == 0) return RTB_OK;
-    k_quantize<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(d_rgba, npix, d_rgb);
+    k_quantize<<<(unsigned)((npix + 1023) / 1024), 256, 0, stream>>>(d_rgba, npix, d_rgb);       // 4 pixels per thread
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }
 
-int rtb_launch_peer_reduce(const float4* const* d_bufs_on_device, int n_bufs, float inv_spp, uint64_t first,
+int rtb_launch_peer_reduce(const RtbPeerBufs& bufs, int n_bufs, float inv_spp, uint64_t first,
                            uint64_t count, float4* d_out, cudaStream_t stream) {
     if (count == 0) return RTB_OK;
-    k_peer_reduce<<<148 * 8, 256, 0, stream>>>(d_bufs_on_device, n_bufs, inv_spp, first, count, d_out);
+    k_peer_reduce<<<148 * 8, 256, 0, stream>>>(bufs, n_bufs, inv_spp, first, count, d_out);
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }

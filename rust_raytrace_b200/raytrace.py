@@ -414,7 +414,9 @@ class B200RayCaster:
         self._n_gpus = None
 
     def _init(self, threads):
-        n = int(threads)
+        """`threads` (main.rs:83 passes 16) as a GPU count: 0 = all visible devices, more than exist is clamped."""
+        visible = check(lib().rtb_visible_device_count(), "rtb_visible_device_count")
+        n = min(int(threads) if int(threads) > 0 else visible, visible, _lib.RTB_MAX_GPUS)
         if self._n_gpus != n:
             check(lib().rtb_init(n, None), "rtb_init")
             self._n_gpus = n

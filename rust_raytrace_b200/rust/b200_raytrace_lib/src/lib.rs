@@ -75,6 +75,7 @@ pub struct RtbStats {
     pub node_tests_bounce: u64,
     pub tri_tests_bounce: u64,
     pub ms_stage: [f64; 4],
+    pub ms_reduce: f64,
 }
 
 #[repr(C)]
@@ -84,6 +85,7 @@ pub struct RtbSceneOpaque {
 
 extern "C" {
     fn rtb_init(n_gpus: c_int, device_ids: *const c_int) -> c_int;
+    fn rtb_visible_device_count() -> c_int;
     fn rtb_last_error() -> *const c_char;
     fn rtb_scene_create(tris: *const RtbTriangle, n: u32, root_orig: *const f32, root_len2: f32,
                         out: *mut *mut RtbSceneOpaque) -> c_int;
@@ -171,16 +173,50 @@ pub fn view_from_viewport(v: &Viewport, seed: u64) -> RtbView {
     }
 }
 
+pub const RTB_MAX_GPUS: usize = 8;
+
 struct Uploaded {
     handle: *mut RtbSceneOpaque,
-    tris_ptr: usize,
-    tris_len: usize,
-    n_gpus: usize,
+    key: SceneKey,
 }
 unsafe impl Send for Uploaded {}
 
-/// The caster.  `threads` of `walk_rays` is reinterpreted as the number of GPUs (0 = all visible).
-/// The uploaded scene (device SoA + LBVH) is cached across frames, keyed by the address and length of `Scene.tris`.
+/// What the cached device scene was built from.  Address and length of `Scene.tris` alone would hand out a stale scene
+/// after an in-place edit or a new `Vec` at the old address, so the key carries a hash of the flattened triangle bytes and
+/// the octree root cube the visibility cull uses (raytrace.rs:795-805).  Hashing 6,721 triangles costs ~10 us per frame.
+#[derive(Clone, Copy, PartialEq, Eq)]
+struct SceneKey {
+    n_tris: usize,
+    content: u64,
+    root: [u32; 4],
+    n_gpus: usize,
+}
+
+fn fnv1a(bytes: &[u8]) -> u64 {
+    let mut h: u64 = 0xcbf29ce484222325;
+    for chunk in bytes.chunks(8) {
+        let mut w = [0u8; 8];
+        w[..chunk.len()].copy_from_slice(chunk);
+        h = (h ^ u64::from_le_bytes(w)).wrapping_mul(0x100000001b3);
+    }
+    h
+}
+
+/// `threads` of `walk_rays` (main.rs:83 passes 16) reinterpreted as a GPU count: 0 = all visible devices, anything larger
+/// than what exists is clamped — never an error.
+fn gpu_count(threads: usize) -> Result<usize, String> {
+    let visible = unsafe { rtb_visible_device_count() };
+    if visible <= 0 {
+        return Err(last_error());
+    }
+    let visible = visible as usize;
+    let want = if threads == 0 { visible } else { threads };
+    Ok(want.min(visible).min(RTB_MAX_GPUS))
+}
+
+/// The caster.  `threads` of `walk_rays` is reinterpreted as the number of GPUs (0 = all visible, clamped to what exists).
+/// The uploaded scene (device SoA + LBVH) is cached across frames, keyed by the CONTENT of `Scene.tris` and the root cube;
+/// `invalidate()` drops it explicitly.
 pub struct B200RayCaster {
     pub seed: u64,
     /// samples of a multi-spp frame are partitioned over the GPUs and reduced over NVLink (rtb_render_progressive)
@@ -189,9 +225,11 @@ pub struct B200RayCaster {
     /// (raytrace.rs:1203-1224) on; the current `Scene` has no `lights` field to carry it
     pub light: Option<([f32; 3], f32)>,
     cache: Mutex<Option<Uploaded>>,
-    /// (address, bytes) of the caller's image buffer currently pinned with rtb_host_register: pinning 133 MB costs
-    /// milliseconds, so it is done once per buffer, not once per frame
-    pinned: Mutex<Option<(usize, usize)>>,
+    /// Pin the caller's image buffer (cudaHostRegister) for the duration of each call: full D2H speed, but registering
+    /// 133 MB costs milliseconds per frame.  The registration never outlives `walk_rays_internal` — the caller owns the
+    /// `Vec` and may free or move it at any time afterwards.  A caller that renders many frames into one buffer should
+    /// pin it itself once (`pin_buffer` / `unpin_buffer`) and leave this off.
+    pub pin_per_call: bool,
 }
 
 unsafe impl Send for B200RayCaster {}
@@ -199,14 +237,40 @@ unsafe impl Sync for B200RayCaster {}
 
 impl B200RayCaster {
     pub fn new() -> Self {
-        B200RayCaster { seed: 0, progressive: false, light: None, cache: Mutex::new(None), pinned: Mutex::new(None) }
+        B200RayCaster { seed: 0, progressive: false, light: None, cache: Mutex::new(None), pin_per_call: false }
     }
 
-    fn scene_handle(&self, s: &Scene, n_gpus: usize) -> Result<*mut RtbSceneOpaque, String> {
+    /// Forget the cached device scene (the next frame uploads and builds again).
+    pub fn invalidate(&self) {
+        if let Some(u) = self.cache.lock().unwrap().take() {
+            unsafe { rtb_scene_destroy(u.handle) };
+        }
+    }
+
+    /// Caller-owned pinning of an image buffer that lives across many frames; undo with `unpin_buffer` BEFORE the buffer
+    /// is freed or reallocated.
+    pub fn pin_buffer(data: &mut [Color]) -> bool {
+        unsafe { rtb_host_register(data.as_mut_ptr() as *mut c_void, data.len() * 16) == 0 }
+    }
+    pub fn unpin_buffer(data: &mut [Color]) {
+        unsafe { rtb_host_unregister(data.as_mut_ptr() as *mut c_void) };
+    }
+
+    fn scene_handle(&self, s: &Scene, threads: usize) -> Result<*mut RtbSceneOpaque, String> {
+        let n_gpus = gpu_count(threads)?;
+        let flat: Vec<RtbTriangle> = s.tris.iter().map(flatten_triangle).collect();
+        let bytes = unsafe { std::slice::from_raw_parts(flat.as_ptr() as *const u8, flat.len() * std::mem::size_of::<RtbTriangle>()) };
+        // the octree root cube (pub fields, raytrace.rs:618-623) drives the same visibility cull as :795-805
+        let root = v3(&s.boxes.orig);
+        let key = SceneKey {
+            n_tris: flat.len(),
+            content: fnv1a(bytes),
+            root: [root[0].to_bits(), root[1].to_bits(), root[2].to_bits(), s.boxes.len2.to_bits()],
+            n_gpus,
+        };
         let mut c = self.cache.lock().unwrap();
-        let key = (s.tris.as_ptr() as usize, s.tris.len());
         if let Some(u) = c.as_ref() {
-            if (u.tris_ptr, u.tris_len, u.n_gpus) == (key.0, key.1, n_gpus) {
+            if u.key == key {
                 return Ok(u.handle);
             }
             unsafe { rtb_scene_destroy(u.handle) };
@@ -215,15 +279,12 @@ impl B200RayCaster {
         if unsafe { rtb_init(n_gpus as c_int, std::ptr::null()) } != 0 {
             return Err(last_error());
         }
-        let flat: Vec<RtbTriangle> = s.tris.iter().map(flatten_triangle).collect();
-        // the octree root cube (pub fields, raytrace.rs:618-623) drives the same visibility cull as :795-805
-        let root = v3(&s.boxes.orig);
         let mut h: *mut RtbSceneOpaque = std::ptr::null_mut();
         let rc = unsafe { rtb_scene_create(flat.as_ptr(), flat.len() as u32, root.as_ptr(), s.boxes.len2, &mut h) };
         if rc != 0 {
             return Err(last_error());
         }
-        *c = Some(Uploaded { handle: h, tris_ptr: key.0, tris_len: key.1, n_gpus });
+        *c = Some(Uploaded { handle: h, key });
         Ok(h)
     }
 }
@@ -254,26 +315,10 @@ impl B200RayCaster {
         }
         Ok(st.rays)
     }
-
-    fn pin(&self, ptr: *mut c_void, bytes: usize) {
-        let mut p = self.pinned.lock().unwrap();
-        if *p == Some((ptr as usize, bytes)) {
-            return;
-        }
-        if let Some((old, _)) = p.take() {
-            unsafe { rtb_host_unregister(old as *mut c_void) };
-        }
-        if unsafe { rtb_host_register(ptr, bytes) } == 0 {      // failure only costs D2H speed
-            *p = Some((ptr as usize, bytes));
-        }
-    }
 }
 
 impl Drop for B200RayCaster {
     fn drop(&mut self) {
-        if let Some((old, _)) = self.pinned.lock().unwrap().take() {
-            unsafe { rtb_host_unregister(old as *mut c_void) };
-        }
         if let Some(u) = self.cache.lock().unwrap().take() {
             unsafe { rtb_scene_destroy(u.handle) };
         }
@@ -291,13 +336,17 @@ impl RayCaster for B200RayCaster {
         let mut st = RtbStats::default();
         let bytes = data.len() * 16;
         let p = data.as_mut_ptr() as *mut f32;
-        self.pin(p as *mut c_void, bytes);
+        // registered for this call only (failure only costs D2H speed); see `pin_per_call`
+        let pinned = self.pin_per_call && unsafe { rtb_host_register(p as *mut c_void, bytes) } == 0;
         unsafe {
             let rc = if self.progressive && view.spp > 1 {
                 rtb_render_progressive(h, &view, p, &mut st)
             } else {
                 rtb_render(h, &view, p, std::ptr::null_mut(), std::ptr::null_mut(), &mut st)
             };
+            if pinned {
+                rtb_host_unregister(p as *mut c_void);
+            }
             if rc != 0 {
                 panic!("b200: rtb_render failed: {}", last_error());   // the reference's error convention (unwrap)
             }

@@ -59,6 +59,38 @@ def test_main_scene_bytes_equal_oracle(R, O, teapot_mesh):
         assert R.main_scene(det).tris.tobytes() == O.main_scene_tris(verts, faces, det).tobytes()
 
 
+def test_bench_scene_builders_equal_the_oracles(R, O, teapot_mesh):
+    """bench.py's CPU arms build their scenes with the oracle's own generators (no product import there): the bytes must be
+    the product's — teapot field (config 4), circles scene (config 1 extension), the mesh fixture reader."""
+    verts, faces = teapot_mesh
+    ov, of = O.load_mesh_bin()
+    assert np.array_equal(ov, verts) and np.array_equal(of, faces)
+    assert R.teapot_field_scene(nz=2, ny=3).tris.tobytes() == O.teapot_field_tris(verts, faces, nz=2, ny=3).tobytes()
+    c = R.circles_scene()
+    t, sph, light = O.circles_scene_parts()
+    assert c.tris.tobytes() == t.tobytes() and c.spheres.tobytes() == sph.tobytes() and c.light == light
+
+
+def test_reference_arm_of_the_bench_does_not_load_the_product():
+    """`bench.py --impl reference` must time the oracle alone: nothing of rust_raytrace_b200 (hence not librtb.so) may be
+    imported, and its `config` must be the GPU arm's."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; "
+            "sys.path.insert(0, %r); import bench; bench.main(); "
+            "assert not [m for m in sys.modules if m.startswith('rust_raytrace_b200')], 'product imported'; "
+            "assert not [l for l in open('/proc/self/maps') if 'librtb' in l], 'librtb.so mapped'; "
+            "print('CONFIG ' + json.dumps(bench.workload_config('teapot4k')))" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["config"] == json.loads(lines[1][len("CONFIG "):])
+
+
 @pytest.mark.parametrize("wh", [(64, 64), (640, 480), (2560, 1440), (3840, 2160), (7680, 4320), (333, 217), (1, 1)])
 def test_viewport_bytes_equal_oracle(R, O, wh):
     a, b = R.main_viewport(*wh, maxdepth=5, spp=1), O.main_viewport(*wh, maxdepth=5, spp=1)
