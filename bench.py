@@ -348,8 +348,9 @@ def run_gpu(args):
         return c
 
     # one counted frame: rays, then (STATS kernel variant) node / triangle tests per ray, per phase
-    scratch = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") if shared_frame else None
-    sptr = scratch.data_ptr() if shared_frame else None
+    # (counting / timing renders go to a scratch buffer: the frame buffer keeps what the timed steps produced)
+    scratch = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    sptr = scratch.data_ptr()
     st = _lib.RtbStats()
     render(my_view, C.byref(st), ptr=sptr)
     my_rays = int(st.rays)
@@ -556,7 +557,7 @@ def run_gpu(args):
                         "partition": (f"samples: rank r renders samples [64r/{world}, 64(r+1)/{world}) of the full frame, then NCCL reduce to rank 0"
                                       if by_samples else f"8-row bands, band b -> rank b % {world}; every rank stores into the one frame on GPU 0"),
                         "l2": "flushed between timed iterations (256 MiB fill); the scene is re-read from HBM each step",
-                        "accelerator": os.environ.get("RTB_BVH", "8") + "-wide BVH",
+                        "accelerator": os.environ.get("RTB_BVH", "4") + "-wide BVH",
                         "bvh": {"nodes": info.n_nodes, "leaves": info.n_leaves, "max_leaf": info.max_leaf,
                                 "height": info.tree_height, "prims": info.n_prims, "refs": info.n_refs,
                                 "ms_build": info.ms_build, "ms_upload": info.ms_upload},

@@ -11,6 +11,9 @@ use std::path::PathBuf;
 use std::process::Command;
 
 fn main() {
+    if env::var("CARGO_FEATURE_GPU").is_err() {
+        return;                       // --no-default-features: nothing to compile or link (dump_golden only)
+    }
     let crate_dir = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap());
     let root = env::var("RTB_ROOT")
         .map(PathBuf::from)

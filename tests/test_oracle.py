@@ -1,5 +1,7 @@
 """CPU tests that pin the oracle: the reference's own known-answer test, the structural numbers of
 the reference scene/octree, octree == brute force == oracle-BVH, and the committed golden vectors."""
+import os
+
 import numpy as np
 
 
@@ -140,3 +142,36 @@ def test_geometry_against_the_references_own_render(O, teapot_mesh):
     # the teapot body and the lower-right mirror are where the picture says they are
     assert mine[150:200, 200:300].all() and ref[150:200, 200:300].all()
     assert abs(int(mine[:140, 300:].sum()) - int(ref[:140, 300:].sum())) < 40
+
+
+def test_compare_golden_tool_on_a_dump_in_the_references_format(O, teapot_mesh, tmp_path):
+    """tools/compare_golden.py is what turns a `dump_golden` run of the real reference (nightly Rust, elsewhere) into a
+    verdict on this repository's goldens.  Here the dump is faked from the oracle in the reference's own formats — debug
+    CSV with shortest round-trip floats (debug.rs:16-33) and raw f32 RGBA — so the tool's parsing and comparison are tested:
+    a faithful dump gives `Found 0 errors`, one flipped hit and one nudged hit time are both found."""
+    import subprocess
+    import sys
+    verts, faces = teapot_mesh
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for det, tag in ((False, "shipped"), (True, "det")):
+        sc = O.Scene(O.main_scene_tris(verts, faces, det), O.ACCEL_OCTREE)
+        rgba, prim, t, _ = sc.render(O.main_viewport(64, 64, 5, 1), seed=0, threads=1)
+        with open(tmp_path / f"golden_64x64_{tag}.csv", "w") as fh:
+            fh.write("Pixel_x;Pixel_y;ray_p;ray_v;tri_hit;hit_t;check_tris\n")
+            for r in range(64):
+                for c in range(64):
+                    fh.write(f"{r};{c};0,0,0;0,0,1;{prim[r, c]};{np.float32(t[r, c])};{prim[r, c]}\n")
+        rgba.astype("<f4").tofile(tmp_path / f"golden_64x64_{tag}.rgba")
+    run = lambda: subprocess.run([sys.executable, os.path.join(root, "tools", "compare_golden.py"), str(tmp_path)],
+                                 capture_output=True, text=True)
+    r = run()
+    assert r.returncode == 0 and r.stdout.strip().endswith("Found 0 errors"), r.stdout[-2000:] + r.stderr[-2000:]
+    # corrupt one hit and one hit time of the deterministic dump
+    lines = open(tmp_path / "golden_64x64_det.csv").read().split("\n")
+    hit_rows = [i for i, ln in enumerate(lines) if ln and ln[0].isdigit() and ln.split(";")[4] != "0"]
+    f = lines[hit_rows[0]].split(";"); f[4] = str(int(f[4]) + 1); lines[hit_rows[0]] = ";".join(f)
+    f = lines[hit_rows[1]].split(";"); f[5] = str(np.nextafter(np.float32(f[5]), np.float32(1e9))); lines[hit_rows[1]] = ";".join(f)
+    open(tmp_path / "golden_64x64_det.csv", "w").write("\n".join(lines))
+    r = run()
+    assert r.returncode == 1 and "Hit Mismatch" in r.stdout and "Hit times differ" in r.stdout
+    assert r.stdout.strip().endswith("Found 4 errors")        # each corruption is seen by the npz and the oracle comparison
