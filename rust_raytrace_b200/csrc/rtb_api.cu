@@ -210,7 +210,8 @@ uint64_t owned_pixels(const ViewDev& vd) {
 // counters->rays afterwards (the wavefront counts bounce rays on the device, primaries on the host).
 int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd, float4* d_rgba, uint32_t* d_prim,
                  float* d_t, cudaStream_t st, uint32_t* launches, uint64_t* primary_rays) {
-    if (g.has_spheres || g.ext.has_light)      // EXTENSION scenes: analytic spheres / shadow rays (rtb_ext.cu)
+    const bool is_ext = g.has_spheres || g.ext.has_light;      // EXTENSION scenes: analytic spheres / shadow rays
+    if (is_ext && (vd.flags & RTB_FLAG_MEGAKERNEL))             // their one-kernel renderer (rtb_ext.cu), the A/B baseline
         return rtb_launch_trace_ext(scene_dev(g, n_prims), vd, g.ext, d_rgba, d_prim, d_t, g.d_counters, st, launches);
     if (vd.flags & RTB_FLAG_MEGAKERNEL)
         return rtb_launch_trace(scene_dev(g, n_prims), vd, d_rgba, d_prim, d_t, g.d_counters, st, launches);
@@ -232,8 +233,8 @@ int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd
         for (auto& e : lane.stage_ev) if (!e) RTB_CUDA(cudaEventCreate(&e));
         sev = lane.stage_ev;
     }
-    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, lane.d_ws, &lane.epoch, d_rgba, d_prim, d_t, g.d_counters, st,
-                                launches, sev, lane.stage_ms);
+    return rtb_launch_wavefront(scene_dev(g, n_prims), vd, is_ext ? &g.ext : nullptr, lane.d_ws, &lane.epoch, d_rgba, d_prim, d_t,
+                                g.d_counters, st, launches, sev, lane.stage_ms);
 }
 
 int env_int(const char* name, int dflt) {

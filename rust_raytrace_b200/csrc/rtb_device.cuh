@@ -170,6 +170,98 @@ __device__ __forceinline__ int shade_hit(const SceneDev& sc, int slot, float t, 
     return 1;
 }
 
+// ---------------------------------------------------------------------------
+// EXTENSION: analytic spheres and shadow rays, shared by the one-kernel extension renderer
+// (rtb_ext.cu) and the wavefront renderer (rtb_wavefront.cu, EXT variants).  Semantics: header of rtb_ext.cu.
+// ---------------------------------------------------------------------------
+// exact test of one leaf record (sphere or triangle) whose first two float4 are already loaded; `has`/`best` skip
+// candidates that cannot win.  A sphere travels as (0, 0, 0, r*r), (centre, id): told apart by the all-zero normal.
+__device__ __forceinline__ bool prim_test_pre(const float4* __restrict__ q, float4 q0, float4 q1, V3 o, V3 d, bool has,
+                                              float best, float* t_out) {
+    if (q0.x == 0.0f && q0.y == 0.0f && q0.z == 0.0f) {
+        const V3 oc = vsub(o, mk(q1.x, q1.y, q1.z));
+        const float b = vdot(oc, d);
+        const float c = __fsub_rn(vdot(oc, oc), q0.w);
+        const float disc = __fsub_rn(__fmul_rn(b, b), c);
+        if (disc < 0.0f) return false;
+        const float sq = __fsqrt_rn(disc);
+        float t = __fsub_rn(-b, sq);
+        if (t < 0.0f) { t = __fadd_rn(-b, sq); if (t < 0.0f) return false; }
+        if (has && t > best) return false;
+        *t_out = t;
+        return true;
+    }
+    return tri_test_pre(q, q0, q1, o, d, has, best, t_out);
+}
+__device__ __forceinline__ bool prim_test(const float4* __restrict__ q, V3 o, V3 d, bool has, float best, float* t_out) {
+    return prim_test_pre(q, __ldg(q), __ldg(q + 1), o, d, has, best, t_out);
+}
+
+// Geometry of a hit on a triangle or sphere record: the hit point, the normal turned against the ray (Triangle::normal
+// :441-449, outward unit(p - c) for a sphere), and whether the hit lies on a wire-frame edge (:419-422).
+struct ExtHit { V3 p, nn; bool hit_edge; float4 s0, s1; };
+__device__ __forceinline__ ExtHit ext_hit_geometry(const SceneDev& sc, int slot, float t, V3 o, V3 d) {
+    ExtHit e;
+    const float4* q = sc.tri + (size_t)RTB_TRI_F4 * (uint32_t)slot;
+    const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
+    e.s0 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)slot);
+    e.s1 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)slot + 1);
+    const bool is_sphere = (__float_as_uint(e.s1.x) & RTB_PRIM_SPHERE) != 0u;
+    e.p = vadd(vmul(d, t), o);
+    V3 n;
+    e.hit_edge = false;
+    if (is_sphere) {
+        n = vunit(vsub(e.p, mk(q1.x, q1.y, q1.z)));
+    } else {
+        n = mk(q0.x, q0.y, q0.z);
+        const V3 ip = vsub(e.p, mk(q1.x, q1.y, q1.z));
+        const float edge_k = __fsub_rn(1.0f, e.s1.z);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float4 qs = __ldg(q + 2 + i);
+            if (vdot(ip, mk(qs.x, qs.y, qs.z)) > __fmul_rn(qs.w, edge_k)) e.hit_edge = true;
+        }
+    }
+    const bool back = vdot(d, n) > 0.0f;
+    e.nn = back ? vmul(n, -1.0f) : n;
+    return e;
+}
+// LightSource::get_shadow_ray (raytrace.rs:600-610): four RNG draws, a ray from p + n * 0.005 * (rand + 1) towards a random
+// point of the light cube (make_ray normalises the direction again)
+__device__ __forceinline__ void ext_shadow_ray(const ExtParams& ex, const ExtHit& e, Rng& g, V3* so, V3* sd) {
+    const float rx = g.next_f32(), ry = g.next_f32(), rz = g.next_f32();
+    const V3 adj = mk(__fadd_rn(ex.light[0], __fmul_rn(rx, ex.light[3])), __fadd_rn(ex.light[1], __fmul_rn(ry, ex.light[3])),
+                      __fadd_rn(ex.light[2], __fmul_rn(rz, ex.light[3])));
+    const V3 dir = vunit(vsub(adj, e.p));
+    const V3 smudge = vmul(e.nn, __fmul_rn(0.005f, __fadd_rn(g.next_f32(), 1.0f)));
+    *so = vadd(e.p, smudge);
+    *sd = vunit(dir);
+}
+// color_ray (raytrace.rs:1228-1252) with the shadow block live: black instead of the surface colour where `shadowed`.
+// Returns 0 = terminal colour, 1 = bounce: (*color, *alpha) for the mix stack and the next ray (*no, *nd).
+__device__ __forceinline__ int ext_shade(const ExtHit& e, V3 d, bool shadowed, Rng& g, V3* color, float* alpha, V3* no, V3* nd) {
+    if (e.hit_edge) { *color = mk(0.0f, 0.0f, 0.0f); return 0; }   // getsurface: edges are Solid black (:450-459)
+    const uint32_t kind = __float_as_uint(e.s1.x) & 0xffu;
+    *color = shadowed ? mk(0.0f, 0.0f, 0.0f) : mk(e.s0.x, e.s0.y, e.s0.z);
+    if (kind == RTB_SOLID) return 0;
+    *alpha = e.s0.w;
+    if (kind == RTB_MATTE) {                                     // lambertian_ray :292-297
+        const V3 rv = random_vec(g);
+        *no = vadd(e.p, vmul(rv, 0.001f));
+        *nd = vunit(vadd(e.nn, rv));
+    } else {                                                     // reflect_ray :278-290
+        const float ddot = fabsf(vdot(d, e.nn));
+        const V3 dir_p = vmul(e.nn, ddot);
+        const V3 dir_o = vadd(d, dir_p);
+        const V3 reflect = vadd(dir_p, dir_o);
+        const V3 rv = vmul(random_vec(g), e.s1.y);
+        const V3 rd = vunit(vadd(reflect, rv));
+        *no = vadd(e.p, vmul(rd, 0.001f));
+        *nd = vunit(rd);
+    }
+    return 1;
+}
+
 // mix_color(c, sub, a) = c*(1-a) + sub*a  (:299-301)
 __device__ __forceinline__ V3 mix_color(V3 c, V3 sub, float a) {
     return vadd(vmul(c, __fsub_rn(1.0f, a)), vmul(sub, a));

@@ -16,32 +16,14 @@
 //
 // A sphere travels through the builder as a pseudo-`Triangle` (norm = 0, incenter = centre, bounding_r2 = r*r, corners =
 // its AABB, kind | RTB_PRIM_SPHERE) so that the BVH pipeline is unchanged; the leaf test tells the two apart by the
-// all-zero normal.  Scenes that use the extension are rendered by this one-kernel renderer (one thread per pixel, the
-// structure of rtb_trace.cu's k_trace, BVH2 nodes); the wavefront pipeline keeps to the reference's live integrator.
+// all-zero normal.  This file is the one-kernel renderer for such scenes (one thread per pixel, the structure of
+// rtb_trace.cu's k_trace, BVH2 nodes): round 1's only renderer for them, now the A/B baseline (RTB_FLAG_MEGAKERNEL) of the
+// wavefront renderer's EXT variants (rtb_wavefront.cu), which run the same arithmetic from rtb_device.cuh.
 #include "rtb_device.cuh"
 
 using namespace rtbdev;
 
 namespace {
-
-// exact test of one leaf record (sphere or triangle); `has`/`best` skip candidates that cannot win
-__device__ __forceinline__ bool prim_test(const float4* __restrict__ q, V3 o, V3 d, bool has, float best, float* t_out) {
-    const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
-    if (q0.x == 0.0f && q0.y == 0.0f && q0.z == 0.0f) {            // sphere: (0, 0, 0, r*r), (centre, id)
-        const V3 oc = vsub(o, mk(q1.x, q1.y, q1.z));
-        const float b = vdot(oc, d);
-        const float c = __fsub_rn(vdot(oc, oc), q0.w);
-        const float disc = __fsub_rn(__fmul_rn(b, b), c);
-        if (disc < 0.0f) return false;
-        const float sq = __fsqrt_rn(disc);
-        float t = __fsub_rn(-b, sq);
-        if (t < 0.0f) { t = __fadd_rn(-b, sq); if (t < 0.0f) return false; }
-        if (has && t > best) return false;
-        *t_out = t;
-        return true;
-    }
-    return tri_test_pre(q, q0, q1, o, d, has, best, t_out);
-}
 
 struct SlabRay { float ix, iy, iz, ox, oy, oz; };
 __device__ __forceinline__ SlabRay slab_ray(V3 o, V3 d) {
@@ -126,64 +108,20 @@ __device__ Hit traverse(const SceneDev& sc, V3 o, V3 d, uint32_t exclude, unsign
     return h;
 }
 
-// color_ray (raytrace.rs:1199-1254) with the shadow block live and sphere normals.  Returns 0 = terminal colour,
-// 1 = bounce: (*color, *alpha) for the mix stack and the next ray (*no, *nd).
+// color_ray (raytrace.rs:1199-1254) with the shadow block live and sphere normals (pieces in rtb_device.cuh, shared with
+// the wavefront renderer).  Returns 0 = terminal colour, 1 = bounce: (*color, *alpha) for the mix stack and the next ray.
 template <bool STATS>
 __device__ int shade_ext(const SceneDev& sc, const ExtParams& ex, const Hit& h, V3 o, V3 d, Rng& g, V3* color, float* alpha,
                          V3* no, V3* nd, unsigned long long& n_node, unsigned long long& n_tri) {
-    const float4* q = sc.tri + (size_t)RTB_TRI_F4 * (uint32_t)h.slot;
-    const float4 q0 = __ldg(q + 0), q1 = __ldg(q + 1);
-    const float4 s0 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)h.slot);
-    const float4 s1 = __ldg(sc.shade + (size_t)RTB_SHADE_F4 * (uint32_t)h.slot + 1);
-    const uint32_t kind_raw = __float_as_uint(s1.x);
-    const bool is_sphere = (kind_raw & RTB_PRIM_SPHERE) != 0u;
-    const uint32_t kind = kind_raw & 0xffu;
-    const V3 p = vadd(vmul(d, h.t), o);
-    V3 n;
-    bool hit_edge = false;
-    if (is_sphere) {
-        n = vunit(vsub(p, mk(q1.x, q1.y, q1.z)));
-    } else {
-        n = mk(q0.x, q0.y, q0.z);
-        const V3 ip = vsub(p, mk(q1.x, q1.y, q1.z));
-        const float edge_k = __fsub_rn(1.0f, s1.z);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float4 qs = __ldg(q + 2 + i);
-            if (vdot(ip, mk(qs.x, qs.y, qs.z)) > __fmul_rn(qs.w, edge_k)) hit_edge = true;
-        }
-    }
-    const bool back = vdot(d, n) > 0.0f;
-    const V3 nn = back ? vmul(n, -1.0f) : n;
+    const ExtHit e = ext_hit_geometry(sc, h.slot, h.t, o, d);
     bool shadowed = false;
-    if (ex.has_light) {                                          // get_shadow_ray, raytrace.rs:600-610
-        const float rx = g.next_f32(), ry = g.next_f32(), rz = g.next_f32();
-        const V3 adj = mk(__fadd_rn(ex.light[0], __fmul_rn(rx, ex.light[3])), __fadd_rn(ex.light[1], __fmul_rn(ry, ex.light[3])),
-                          __fadd_rn(ex.light[2], __fmul_rn(rz, ex.light[3])));
-        const V3 dir = vunit(vsub(adj, p));
-        const V3 smudge = vmul(nn, __fmul_rn(0.005f, __fadd_rn(g.next_f32(), 1.0f)));
-        const Hit sh = traverse<true, STATS>(sc, vadd(p, smudge), vunit(dir), h.orig, n_node, n_tri);
+    if (ex.has_light) {
+        V3 so, sd;
+        ext_shadow_ray(ex, e, g, &so, &sd);
+        const Hit sh = traverse<true, STATS>(sc, so, sd, h.orig, n_node, n_tri);
         shadowed = sh.slot >= 0;
     }
-    if (hit_edge) { *color = mk(0.0f, 0.0f, 0.0f); return 0; }   // getsurface: edges are Solid black (:450-459)
-    *color = shadowed ? mk(0.0f, 0.0f, 0.0f) : mk(s0.x, s0.y, s0.z);
-    if (kind == RTB_SOLID) return 0;
-    *alpha = s0.w;
-    if (kind == RTB_MATTE) {                                     // lambertian_ray :292-297
-        const V3 rv = random_vec(g);
-        *no = vadd(p, vmul(rv, 0.001f));
-        *nd = vunit(vadd(nn, rv));
-    } else {                                                     // reflect_ray :278-290
-        const float ddot = fabsf(vdot(d, nn));
-        const V3 dir_p = vmul(nn, ddot);
-        const V3 dir_o = vadd(d, dir_p);
-        const V3 reflect = vadd(dir_p, dir_o);
-        const V3 rv = vmul(random_vec(g), s1.y);
-        const V3 rd = vunit(vadd(reflect, rv));
-        *no = vadd(p, vmul(rd, 0.001f));
-        *nd = vunit(rd);
-    }
-    return 1;
+    return ext_shade(e, d, shadowed, g, color, alpha, no, nd);
 }
 
 template <bool STATS>

@@ -213,9 +213,10 @@ int rtb_launch_trace_ext(const SceneDev& sc, const ViewDev& vw, const ExtParams&
 size_t rtb_wf_workspace_bytes(uint32_t n_slots, uint32_t maxdepth, bool multisample);
 // stage_ev (nullable): 5 events recorded at the stage boundaries of every sample; stage_ms accumulates their gaps
 // (this synchronises the stream once per sample: timing mode only).
-int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, void* workspace, uint32_t* epoch, float4* d_rgba,
-                         uint32_t* d_prim, float* d_t, TraceCounters* d_counters, cudaStream_t stream, uint32_t* launches,
-                         cudaEvent_t* stage_ev = nullptr, float* stage_ms = nullptr);
+// ext: non-null for an extension scene (analytic spheres in the leaves and / or a light): the EXT variants of the kernel.
+int rtb_launch_wavefront(const SceneDev& sc, const ViewDev& vw, const ExtParams* ext, void* workspace, uint32_t* epoch,
+                         float4* d_rgba, uint32_t* d_prim, float* d_t, TraceCounters* d_counters, cudaStream_t stream,
+                         uint32_t* launches, cudaEvent_t* stage_ev = nullptr, float* stage_ms = nullptr);
 
 int rtb_launch_quantize(const float4* d_rgba, uint64_t npix, uint8_t* d_rgb, cudaStream_t stream);
 int rtb_launch_scale(float4* d_rgba, uint64_t npix, float inv_spp, cudaStream_t stream);

@@ -644,6 +644,33 @@ def test_circles_scene_analytic_spheres(R, O, spp, light):
     s.release()
 
 
+@pytest.mark.parametrize("spp", [1, 2])
+def test_extension_wavefront_equals_the_one_kernel_renderer(R, O, spp):
+    """Extension scenes (analytic spheres, shadow rays) run on the wavefront renderer's EXT variants: spheres as a leaf
+    record kind, the shadow query as an any-hit ray of the lane's path.  RTB_FLAG_MEGAKERNEL selects round 1's
+    one-thread-per-pixel renderer for them (rtb_ext.cu): same ids, t, colours and ray count — also with
+    RTB_FLAG_BRUTE (no BVH) — and all equal to the oracle; the teapot scene with a light likewise."""
+    from rust_raytrace_b200 import _lib
+    for s, wh, depth in ((R.circles_scene(n=40, seed=5), (640, 360), 4), (R.main_scene(deterministic=False), (400, 225), 5)):
+        if s.spheres is None:
+            s.set_light((6.0, -2.0, 0.0), 0.5)
+        v = R.main_viewport(*wh, depth, spp)
+        a = gpu_render(R, s, v, seed=12, stats=True)
+        vm = _lib.RtbView.from_buffer_copy(v)
+        vm.flags |= _lib.RTB_FLAG_MEGAKERNEL
+        b = gpu_render(R, s, vm, seed=12)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+        assert a[3].total_rays == b[3].total_rays
+        if s.spheres is not None:
+            vb = _lib.RtbView.from_buffer_copy(R.main_viewport(160, 90, depth, spp))
+            vb.flags |= _lib.RTB_FLAG_BRUTE
+            c = gpu_render(R, s, vb, seed=12)
+            d = gpu_render(R, s, R.main_viewport(160, 90, depth, spp), seed=12)
+            assert np.array_equal(c[1], d[1]) and np.array_equal(bits(c[0]), bits(d[0])) and c[3].total_rays == d[3].total_rays
+        assert_bit_exact(a, _oracle_ext(O, s, O.ACCEL_BVH).render(O.main_viewport(*wh, depth, spp), seed=12), "ext wavefront")
+        s.release()
+
+
 def test_sphere_edge_cases(R, O):
     """Camera inside a sphere (far root, back face), a sphere behind the camera (both roots negative), touching
     spheres, a huge sphere around everything; 2K-wide band to cover the config's resolution."""
