@@ -785,7 +785,12 @@ int render_host(rtb_scene* s, const RtbView* view, float* rgba_out, uint8_t* rgb
         // pieces exist to overlap the D2H copy with the kernels: 16 B/px need 8 of them, the 3 B/px of the quantised frame
         // only 3 (4K frame through rtb_render_rgb8: 2.37 ms with 3 pieces, 2.42 with 4, 2.51 with 8, 2.57 with 2)
         const size_t dflt_pieces = rgb8_out ? RTB_DEFAULT_PIECES_RGB8 : RTB_DEFAULT_PIECES;
-        const uint32_t pieces = (uint32_t)env_int("RTB_PIECES", (int)std::min<size_t>(dflt_pieces, std::max<size_t>(1, pixels / (1u << 20))));
+        // a piece of the f32 frame should not be much smaller than 256 K pixels (its kernels' fixed tails), a piece of the
+        // quantised frame not smaller than 1 M (the copy it overlaps is short).  With several GPUs the copies share the host's
+        // memory path (8 GPUs: 133 MB come home in 1.24 ms however they are issued), so what counts is how soon the FIRST
+        // copy starts: 4 pieces per GPU at N = 8 instead of one.
+        const size_t per_piece = rgb8_out ? (1u << 20) : (1u << 18);
+        const uint32_t pieces = (uint32_t)env_int("RTB_PIECES", (int)std::min<size_t>(dflt_pieces, std::max<size_t>(1, pixels / per_piece)));
         const uint32_t n_lanes = (uint32_t)env_int("RTB_LANES", RTB_DEFAULT_LANES);
         RTB_CUDA(cudaMemsetAsync(g.d_counters, 0, sizeof(TraceCounters), g.stream));
         RTB_CUDA(cudaEventRecord(g.ev0, g.stream));
