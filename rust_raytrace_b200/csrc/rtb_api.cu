@@ -192,6 +192,7 @@ SceneDev scene_dev(const GpuScene& g, uint32_t n_prims) {
     s.nodes4 = g.d_nodes4;
     s.stack4 = g.stack4_need ? g.stack4_need + 1u : 3u * (g.depth4 + 1u) + 2u;    // exact bound from the builder, else 3 per level
     s.nodes8 = g.d_nodes8; s.tri8 = g.d_tri8; s.shade8 = g.d_shade8; s.depth8 = g.depth8;
+    s.n_nodes4 = g.n_nodes4; s.n_nodes8 = g.n_nodes8;
     return s;
 }
 

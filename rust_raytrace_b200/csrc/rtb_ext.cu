@@ -97,6 +97,7 @@ __device__ Hit traverse(const SceneDev& sc, V3 o, V3 d, uint32_t exclude, unsign
         }
         if (next1 != 0xffffffffu) {
             if (tn1 < tn0) { const uint32_t s = next0; next0 = next1; next1 = s; }
+            RTB_DASSERT(sp < RTB_STACK && next1 + 1u < sc.n_nodes);
             stack[sp++] = next1;
             node = next0;
             continue;

@@ -37,12 +37,24 @@ struct SceneDev {
     uint32_t height;     // tree height: the traversal stack never holds more than `height` entries
     const float4* nodes4;   // 4-wide collapse of the same tree: 8 x float4 (128 B) per node, see rtb_lbvh.cu
     uint32_t stack4;     // stack entries a BVH4 traversal can need: 3 per level
+    uint32_t n_nodes4, n_nodes8;   // node counts (bounds of the RTB_DEBUG checks)
     // 8-wide compressed collapse (80 B per node) with its own reference order: tri8 / shade8 are tri / shade permuted
     const uint4* nodes8;
     const float4* tri8;
     const float4* shade8;
     uint32_t depth8;     // levels of the BVH8: its traversal stack holds at most one entry per level
 };
+
+// RTB_DEBUG build (make debug -> librtb_debug.so): device-side bounds checks on everything the traversal indexes — node and
+// reference indices, traversal-stack depth, queue and pixel-slot indices.  compute-sanitizer is not available on the
+// B200 pool this was developed on; a tripped check ends the kernel with cudaErrorAssert, which the C ABI reports as
+// RTB_ERR_CUDA.  tests/test_gpu_parity.py runs a parity frame of every renderer through the debug library.
+#ifdef RTB_DEBUG
+#include <cassert>
+#define RTB_DASSERT(cond) assert(cond)
+#else
+#define RTB_DASSERT(cond) ((void)0)
+#endif
 
 #define RTB_TRI_F4 5
 #define RTB_SHADE_F4 2

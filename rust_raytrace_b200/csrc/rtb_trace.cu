@@ -116,6 +116,7 @@ __device__ __forceinline__ Hit closest_hit(const SceneDev& sc, V3 o, V3 d, bool 
         if (next1 != 0xffffffffu) {
             // both internal: near one first, far one on the stack
             if (tn1 < tn0) { uint32_t s = next0; next0 = next1; next1 = s; }
+            RTB_DASSERT(sp < RTB_STACK && next1 + 1u < sc.n_nodes);
             stack[sp++] = next1;
             node = next0;
             continue;

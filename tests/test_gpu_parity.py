@@ -257,6 +257,16 @@ def test_root_cube_cull(R, O):
     assert R.Scene(arr).info().n_prims == 1 and R.Scene(arr, boxes=None).info().n_prims == 2
 
 
+def test_cell_spanning_triangles_vs_the_reference_octree(R, O):
+    """Triangles that span most of the octree root cube (tests/test_oracle.py::large_triangle_scene): the GPU path against
+    the reference-algorithm (octree) oracle, mirror bounces included."""
+    from test_oracle import large_triangle_scene
+    tris = large_triangle_scene(O)
+    v, ov = R.main_viewport(320, 240, 4, 1), O.main_viewport(320, 240, 4, 1)
+    assert_bit_exact(gpu_render(R, R.Scene(tris.view(R.raytrace.TRI_DTYPE)), v, seed=2),
+                     O.Scene(tris, O.ACCEL_OCTREE).render(ov, seed=2), "cell-spanning triangles")
+
+
 def test_sphere_scene_config1(R, O):
     """BASELINE config 1 ('circles'): tessellated spheres (make_sphere, raytrace.rs:464-529) over a disk,
     primary + one bounce.  The analytic-sphere scene of circles_2k.png no longer exists in the reference."""
@@ -739,3 +749,45 @@ def test_all_three_bvh_builders_give_the_same_frame(R, tmp_path):
         outs.append((open(out, "rb").read(), rays))
     assert all(o == outs[0] for o in outs[1:])
 
+
+
+def test_debug_build_runs_clean(R, O, scenes, tmp_path):
+    """librtb_debug.so (make debug: -DRTB_DEBUG, device-side bounds asserts on node / reference / stack / queue / slot
+    indices — the stand-in for compute-sanitizer, which the GPU pool refuses) renders a frame through every renderer
+    variant without tripping an assert, and the frames are the release library's."""
+    import os
+    import subprocess
+    import sys
+    from rust_raytrace_b200 import _lib
+    dbg = os.path.join(os.path.dirname(_lib.LIB_PATH), "librtb_debug.so")
+    assert os.path.exists(dbg), "librtb_debug.so missing: __graft_entry__.build() makes it"
+    code = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+import rust_raytrace_b200 as R
+from rust_raytrace_b200 import _lib
+assert _lib.LIB_PATH.endswith("librtb_debug.so")
+s = R.main_scene(False)
+out = []
+for fl in (0, _lib.RTB_FLAG_FUSED, _lib.RTB_FLAG_BVH8, _lib.RTB_FLAG_MEGAKERNEL, _lib.RTB_FLAG_STATS):
+    v = R.main_viewport(333, 217, 5, 2); v.flags = fl
+    data = R.new_image(v)
+    c = R.B200RayCaster(want_ids=True, seed=3); c.walk_rays(v, s, data)
+    out.append(hashlib.sha256(data.tobytes() + c.prim.tobytes()).hexdigest())
+e = R.circles_scene(n=30, seed=2)
+for fl in (0, _lib.RTB_FLAG_MEGAKERNEL):
+    v = R.main_viewport(200, 120, 3, 1); v.flags = fl
+    data = R.new_image(v); R.B200RayCaster(seed=3).walk_rays(v, e, data)
+    out.append(hashlib.sha256(data.tobytes()).hexdigest())
+print("HASHES", " ".join(out))
+""" % os.path.dirname(os.path.dirname(_lib.LIB_PATH))
+    res = {}
+    for tag, lib in (("release", _lib.LIB_PATH), ("debug", dbg)):
+        env = dict(os.environ, RTB_LIB=lib, RTB_BVH8="1", RTB_EXT_WAVEFRONT_MIN="0")
+        r = subprocess.run([sys.executable, "-c", code.replace('assert _lib.LIB_PATH.endswith("librtb_debug.so")', "" if tag == "release" else 'assert _lib.LIB_PATH.endswith("librtb_debug.so")')],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-3000:]
+        res[tag] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASHES")][0]
+    assert res["debug"] == res["release"]
+    h = res["release"].split()[1:]
+    assert len(set(h[:5])) == 1 and h[5] == h[6]          # every renderer variant: the same frame

@@ -175,3 +175,38 @@ def test_compare_golden_tool_on_a_dump_in_the_references_format(O, teapot_mesh, 
     r = run()
     assert r.returncode == 1 and "Hit Mismatch" in r.stdout and "Hit times differ" in r.stdout
     assert r.stdout.strip().endswith("Found 4 errors")        # each corruption is seen by the npz and the oracle comparison
+
+
+def large_triangle_scene(O):
+    """Two triangles that span most of the octree root cube (tens of cells at every level) over 400 small ones that make
+    the octree subdivide: the case where the reference's box_contains_polygon (corner / centroid in cube, then six
+    face-plane line tests, raytrace.rs:645-779) — which is not a conservative triangle/box overlap test — could lose a
+    triangle from a cell, so that the octree misses a hit a conservative accelerator finds."""
+    S = O.Surface
+    parts = [O.make_dummy_triangle(),
+             O.make_triangle([[-6, -14, 6], [9, -2, 30], [-3, 15, 12]], S(O.OR_SOLID, O.make_color(200, 50, 50)), 0.0),
+             O.make_triangle([[8, -12, 25], [-8, 3, 8], [7, 13, 20]], S(O.OR_REFLECTIVE, O.make_color(50, 200, 50), 0.5, 0.0), 0.0)]
+    rng = np.random.RandomState(3)
+    for _ in range(400):
+        c = np.array([rng.uniform(-3, 5), rng.uniform(-6, 6), rng.uniform(4, 16)], np.float32)
+        p = [c + rng.uniform(-.25, .25, 3).astype(np.float32) for _ in range(3)]
+        try:
+            parts.append(O.make_triangle(p, S(O.OR_SOLID, O.make_color(*[int(x) for x in rng.randint(30, 255, 3)])), 0.0))
+        except ValueError:
+            pass
+    return np.concatenate(parts)
+
+
+def test_octree_equals_bruteforce_with_cell_spanning_triangles(O):
+    """Quantifies the divergence the GPU path could show against the REFERENCE's octree on scenes unlike the teapot: none
+    on this one — octree, brute force and the oracle BVH return the same ids, t and colours on all 76,800 pixels, bounces
+    included (INTEGRATION.md, "Where the results could differ")."""
+    tris = large_triangle_scene(O)
+    v = O.main_viewport(320, 240, 4, 1)
+    octree = O.Scene(tris, O.ACCEL_OCTREE)
+    assert octree.tree_stats().nodes > 100
+    a = octree.render(v, seed=2)
+    for accel in (O.ACCEL_TRIVIAL, O.ACCEL_BVH):
+        b = O.Scene(tris, accel).render(v, seed=2)
+        assert int((a[1] != b[1]).sum()) == 0 and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+    assert len(np.unique(a[1])) > 50 and (a[1] == 1).sum() > 1000 and (a[1] == 2).sum() > 1000

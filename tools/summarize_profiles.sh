@@ -7,15 +7,17 @@ OUT=profiles
 mkdir -p $OUT
 cp $IN/${TAG}_bench.json $OUT/${TAG}_bench.json
 grep -v "^==" $IN/${TAG}_launches.csv > $OUT/${TAG}_launches.csv || true
-for K in k_wf_bounce k_wf_trace; do
-  ncu -i $IN/${TAG}_$K.ncu-rep --page details 2>/dev/null | grep -v "^ *$" > $OUT/${TAG}_${K}_details.txt
-  python tools/ncu_lines.py $IN/${TAG}_$K.ncu-rep 50 > $OUT/${TAG}_${K}_lines.txt
-  ncu -i $IN/${TAG}_$K.ncu-rep --page raw --csv 2>/dev/null | python -c "
+k=0
+for PHASE in primary bounce; do
+  ncu -i $IN/${TAG}_k_wf_path.ncu-rep --launch-skip $k --launch-count 1 --page details 2>/dev/null | grep -v "^ *$" > $OUT/${TAG}_k_wf_path_${PHASE}_details.txt
+  ncu -i $IN/${TAG}_k_wf_path.ncu-rep --launch-skip $k --launch-count 1 --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); h=rows[0]; u=rows[1]; v=rows[2]
-want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','smsp__inst_executed.sum','smsp__thread_inst_executed_per_inst_executed.ratio','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__t_sector_hit_rate.pct','lts__t_sector_hit_rate.pct','launch__registers_per_thread','launch__grid_size','launch__block_size','launch__shared_mem_per_block_dynamic','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','l1tex__throughput.avg.pct_of_peak_sustained_active','lts__throughput.avg.pct_of_peak_sustained_elapsed','dram__throughput.avg.pct_of_peak_sustained_elapsed','sm__throughput.avg.pct_of_peak_sustained_elapsed']
+want=['Kernel Name','gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','smsp__inst_executed.sum','smsp__thread_inst_executed_per_inst_executed.ratio','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__t_sector_hit_rate.pct','lts__t_sector_hit_rate.pct','launch__registers_per_thread','launch__grid_size','launch__block_size','launch__shared_mem_per_block_dynamic','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','l1tex__throughput.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts.sum','lts__throughput.avg.pct_of_peak_sustained_elapsed','dram__throughput.avg.pct_of_peak_sustained_elapsed','sm__throughput.avg.pct_of_peak_sustained_elapsed']
 for w in want:
     if w in h: print(f'{w},{u[h.index(w)]},{v[h.index(w)]}')
-" > $OUT/${TAG}_${K}_raw.csv
+" > $OUT/${TAG}_k_wf_path_${PHASE}_raw.csv
+  k=$((k+1))
 done
+python tools/ncu_lines.py $IN/${TAG}_k_wf_path.ncu-rep 50 > $OUT/${TAG}_k_wf_path_lines.txt
 ls -la $OUT | grep ${TAG}
