@@ -51,7 +51,7 @@ WORKLOADS = {
                  3840, 2160, 5, 1, "bands"),
     # configs[0]: the "circles" scene — not in the mounted reference; analytic spheres + shadow rays are
     # this build's extension (EXT variants of the wavefront kernel; this 224-primitive scene runs on the one-kernel
-    # renderer, which is faster below ~1,000 primitives), checked against the oracle's restatement of the same
+    # renderer, which is faster for scenes of a few thousand references or fewer), checked against the oracle's restatement of the same
     "circles2k": ("circles 2K (extension): 64 analytic spheres + ground disk + one cube light, 2560x1440, maxdepth 2 "
                   "(primary + 1 bounce) + one shadow ray per hit, 1 spp", 2560, 1440, 2, 1, "bands"),
     # configs[3]: ~1M triangles, GPU LBVH build + incoherent (mirror) bounces
@@ -528,7 +528,7 @@ def run_gpu(args):
         # (extension scenes run the EXT variant of the same kernel: its tests include the shadow rays', its rays do not)
         dom_kernel, b_rays = "k_wf_path<bounce phase>", max(int(st2.bounce_rays), 1)
         nb_node, nb_tri = st2.node_tests_bounce / b_rays, st2.tri_tests_bounce / b_rays
-        if name == "circles2k":      # 224 primitives: below the wavefront threshold, one kernel per frame (rtb_ext.cu)
+        if name == "circles2k":      # 224 primitives (~1,500 references): below the wavefront threshold, one kernel per frame (rtb_ext.cu)
             dom_kernel, b_rays, nb_node, nb_tri = "k_trace_ext", max(int(st2.rays), 1), n_node, n_tri
             stage_ms = np.array([0.0, 0.0, 0.0, ms_mine])
         elif stage_ms[3] < stage_ms[1]:           # the primary phase dominates (maxdepth 2): report that launch

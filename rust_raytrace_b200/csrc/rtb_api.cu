@@ -212,14 +212,14 @@ uint64_t owned_pixels(const ViewDev& vd) {
 int launch_frame(GpuScene& g, GpuLane& lane, uint32_t n_prims, const ViewDev& vd, float4* d_rgba, uint32_t* d_prim,
                  float* d_t, cudaStream_t st, uint32_t* launches, uint64_t* primary_rays) {
     const bool is_ext = g.has_spheres || g.ext.has_light;      // EXTENSION scenes: analytic spheres / shadow rays
-    // Their default renderer is the wavefront kernel's EXT variant, except for tiny scenes: with a few hundred primitives a
+    // Their default renderer is the wavefront kernel's EXT variant, except for small scenes: with a few hundred primitives a
     // ray costs a handful of node visits and the per-path queue traffic of the wavefront design outweighs what it saves
-    // (B200, circles scene, 224 primitives, 2K, maxdepth 2 / 3 / 5: one kernel 0.58 / 0.83 / 1.35 ms, wavefront 0.79 /
+    // (B200, circles scene, 224 primitives = ~1,500 references, 2K, maxdepth 2 / 3 / 5: one kernel 0.58 / 0.83 / 1.35 ms, wavefront 0.79 /
     // 1.06 / 1.50 ms; teapot scene + light, 7,120 references, 4K: one kernel 5.34 ms, wavefront 3.93 ms).
     // RTB_EXT_WAVEFRONT_MIN (references, read per call) moves the threshold; RTB_FLAG_MEGAKERNEL forces the one-kernel renderer.
     if (is_ext) {
         const char* e = getenv("RTB_EXT_WAVEFRONT_MIN");
-        const uint32_t min_refs = e ? (uint32_t)std::max(0, atoi(e)) : 1024u;
+        const uint32_t min_refs = e ? (uint32_t)std::max(0, atoi(e)) : 4096u;
         if ((vd.flags & RTB_FLAG_MEGAKERNEL) || n_prims < min_refs)
             return rtb_launch_trace_ext(scene_dev(g, n_prims), vd, g.ext, d_rgba, d_prim, d_t, g.d_counters, st, launches);
     }

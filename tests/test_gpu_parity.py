@@ -657,7 +657,7 @@ def test_circles_scene_analytic_spheres(R, O, spp, light):
 @pytest.mark.parametrize("spp", [1, 2])
 def test_extension_wavefront_equals_the_one_kernel_renderer(R, O, spp, monkeypatch):
     """Extension scenes (analytic spheres, shadow rays) run on the wavefront renderer's EXT variants: spheres as a leaf
-    record kind, the shadow query as an any-hit ray of the lane's path (scenes of fewer than 1,024 references default to
+    record kind, the shadow query as an any-hit ray of the lane's path (scenes of fewer than 4,096 references default to
     the one-kernel renderer, so the threshold is lowered here).  RTB_FLAG_MEGAKERNEL selects round 1's one-thread-per-pixel
     renderer (rtb_ext.cu): same ids, t, colours and ray count — also with RTB_FLAG_BRUTE (no BVH) — and all equal to the
     oracle; the teapot scene with a light likewise."""
