@@ -7,6 +7,7 @@ stochastic materials are ALSO compared bit for bit; the PSNR test covers the cas
 summation order legitimately differs (samples partitioned over GPUs).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -376,6 +377,58 @@ def test_band_partition_assembles_the_single_gpu_frame(R, scenes, world):
     n = L.rtb_partition_rows(H, 1, world, rows.ctypes.data, H)
     written = (~torch.isnan(alone[..., 0])).any(dim=1).cpu().numpy()
     assert sorted(np.flatnonzero(written).tolist()) == rows[:n].tolist()
+
+
+def test_two_processes_render_into_one_frame_over_ipc(R, scenes, tmp_path):
+    """The one-process-per-GPU shape of bench.py on ONE GPU: the parent allocates the frame (rtb_device_alloc), exports it
+    (rtb_ipc_export) and renders band rank 0 of 2; a child PROCESS maps it (rtb_ipc_open) and renders rank 1 of 2 straight
+    into the parent's memory.  The assembled frame must be the single-rank frame bit for bit."""
+    import subprocess
+    import sys
+    import torch
+    from rust_raytrace_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.rtb_init(1, None), "rtb_init")
+    s = scenes[False][0]
+    h = s.upload()
+    W, H = 1283, 721
+    v = R.main_viewport(W, H, 5, 1)
+    v.seed = 8
+    frame = C.c_void_p()
+    _lib.check(L.rtb_device_alloc(0, W * H * 16, C.byref(frame)), "rtb_device_alloc")
+    hbuf = C.create_string_buffer(64)
+    _lib.check(L.rtb_ipc_export(frame, hbuf), "rtb_ipc_export")
+    st = _lib.RtbStats()
+    _lib.check(L.rtb_render_device(h, C.byref(v), 0, 0, 2, frame, None, None, None, C.byref(st)), "render rank 0")
+    child = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import rust_raytrace_b200 as R
+from rust_raytrace_b200 import _lib
+L = _lib.lib(); _lib.check(L.rtb_init(1, None), "init")
+s = R.main_scene(False); h = s.upload()
+v = R.main_viewport(%d, %d, 5, 1); v.seed = 8
+p = C.c_void_p()
+_lib.check(L.rtb_ipc_open(0, bytes.fromhex(sys.argv[1]), C.byref(p)), "rtb_ipc_open")
+st = _lib.RtbStats()
+_lib.check(L.rtb_render_device(h, C.byref(v), 0, 1, 2, p, None, None, None, C.byref(st)), "render rank 1")
+_lib.check(L.rtb_ipc_close(0, p), "rtb_ipc_close")
+print("RAYS", st.rays)
+""" % (os.path.dirname(os.path.dirname(_lib.LIB_PATH)), W, H)
+    r = subprocess.run([sys.executable, "-c", child, hbuf.raw.hex()], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rays = int(st.rays) + int([ln for ln in r.stdout.splitlines() if ln.startswith("RAYS")][0].split()[1])
+    one = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    st1 = _lib.RtbStats()
+    _lib.check(L.rtb_render_device(h, C.byref(v), 0, 0, 1, one.data_ptr(), None, None, None, C.byref(st1)), "render whole")
+
+    class Dev:
+        __cuda_array_interface__ = {"shape": (H, W, 4), "typestr": "<f4", "data": (frame.value, False), "version": 2}
+    both = torch.as_tensor(Dev(), device="cuda")
+    torch.cuda.synchronize()
+    assert torch.equal(both.view(torch.int32), one.view(torch.int32)) and rays == int(st1.rays)
+    del both
+    _lib.check(L.rtb_device_free(0, frame), "rtb_device_free")
 
 
 def test_config5_8k_band_64spp_partitioned_psnr(R, O, scenes):
