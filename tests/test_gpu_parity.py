@@ -258,6 +258,57 @@ def test_root_cube_cull(R, O):
     assert R.Scene(arr).info().n_prims == 1 and R.Scene(arr, boxes=None).info().n_prims == 2
 
 
+def _random_scene(R, rng, n_tris, inside_root_cube=True):
+    """A triangle soup in main.rs's octree root cube ((0, 0, 20.1) +- 20): sizes from slivers to triangles spanning a third of
+    the cube, every SurfaceKind, wire-frame edges on some.  inside_root_cube=False lets triangles stick out of the cube: the
+    reference's octree then sees their outer parts only from some directions (tests/test_oracle.py)."""
+    parts = [R.make_dummy_triangle()]
+    while len(parts) <= n_tris:
+        c = np.array([rng.uniform(-6, 8), rng.uniform(-9, 9), rng.uniform(3, 30)], np.float32)
+        size = float(10 ** rng.uniform(-1.3, 0.9))
+        p = [c + (rng.uniform(-1, 1, 3) * size * (0.05 if (k == 2 and rng.rand() < 0.15) else 1.0)).astype(np.float32) for k in range(3)]
+        if inside_root_cube and any(abs(q[0]) > 19.5 or abs(q[1]) > 19.5 or not (0.6 <= q[2] <= 39.6) for q in p):
+            continue
+        col = R.make_color(tuple(int(x) for x in rng.randint(0, 256, 3)))
+        kind = rng.randint(0, 3)
+        surf = (R.SurfaceKind.Solid(col) if kind == 0 else R.SurfaceKind.Matte(col, float(rng.uniform(0.05, 0.9))) if kind == 1
+                else R.SurfaceKind.Reflective(float(rng.choice([0.0, 0.001, 0.05])), col, float(rng.uniform(0.1, 0.9))))
+        try:
+            parts.append(R.make_triangle(p, surf, float(rng.choice([-1.0, 0.0, 0.03, 0.2]))))
+        except ValueError:
+            pass                                   # a degenerate draw: the reference would panic, skip it
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scenes_differential(R, O, seed):
+    """Randomised differential test against the oracle: random triangle soups (2 .. 600 triangles, all three surface
+    kinds, slivers and cube-spanning triangles), random cameras (position, direction, roll, field of view), odd image sizes
+    (the centre pixel's ray runs exactly along the view axis: zero direction components in the slab test), maxdepth 1..8,
+    1..3 samples — ids, t, RGBA and ray counts bit-exact against the oracle BVH AND the reference-algorithm octree (the soups
+    lie inside the root cube; what happens when triangles stick out of it: tests/test_oracle.py)."""
+    rng = np.random.RandomState(1000 + seed)
+    n_tris = int(rng.choice([2, 5, 17, 60, 200, 600]))
+    tris = _random_scene(R, rng, n_tris)
+    w, h = int(rng.choice([33, 101, 161, 257])), int(rng.choice([31, 75, 121]))
+    maxdepth, spp = int(rng.randint(1, 9)), int(rng.choice([1, 1, 2, 3]))
+    if seed % 3 == 0:          # looking straight down +z from inside the cube: axis-parallel centre ray
+        pos, dirv, roll = [float(rng.uniform(-1, 3)), float(rng.uniform(-2, 2)), 0.0], [0.0, 0.0, 1.0], 0.0
+    else:
+        pos = [float(rng.uniform(-4, 6)), float(rng.uniform(-6, 6)), float(rng.uniform(-3, 2))]
+        dirv = [float(rng.uniform(-0.5, 0.5)), float(rng.uniform(-0.5, 0.5)), 1.0]
+        roll = float(rng.uniform(-0.6, 0.6))
+    fov = float(rng.choice([40.0, 90.0, 120.0]))
+    args = ((w, h), (1.0, h / w), pos)
+    v = R.create_viewport(*args, R.unit(dirv), fov, roll, maxdepth, spp)
+    ov = O.create_viewport(*args, O.unit(dirv), fov, roll, maxdepth, spp)
+    sc = R.Scene(tris)
+    got = gpu_render(R, sc, v, seed=seed)
+    assert_bit_exact(got, O.Scene(tris.view(O.TRI_DTYPE), O.ACCEL_BVH).render(ov, seed=seed), f"random scene {seed} ({n_tris} tris, {w}x{h}, depth {maxdepth}, spp {spp})")
+    assert_bit_exact(got, O.Scene(tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE).render(ov, seed=seed), f"random scene {seed} vs octree")
+    sc.release()
+
+
 def test_cell_spanning_triangles_vs_the_reference_octree(R, O):
     """Triangles that span most of the octree root cube (tests/test_oracle.py::large_triangle_scene): the GPU path against
     the reference-algorithm (octree) oracle, mirror bounces included."""

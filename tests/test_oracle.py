@@ -3,6 +3,7 @@ the reference scene/octree, octree == brute force == oracle-BVH, and the committ
 import os
 
 import numpy as np
+import pytest
 
 
 def bits(a):
@@ -210,3 +211,46 @@ def test_octree_equals_bruteforce_with_cell_spanning_triangles(O):
         b = O.Scene(tris, accel).render(v, seed=2)
         assert int((a[1] != b[1]).sum()) == 0 and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
     assert len(np.unique(a[1])) > 50 and (a[1] == 1).sum() > 1000 and (a[1] == 2).sum() > 1000
+
+
+@pytest.mark.parametrize("seed", [1, 3, 6, 10])
+def test_octree_equals_bruteforce_on_random_scenes(R, O, seed):
+    """The argument that lets a different accelerator be primitive-ID exact (closest hit = argmin t, lowest index on ties)
+    on scenes unlike the teapot: random triangle soups of the GPU differential test (tests/test_gpu_parity.py::_random_scene,
+    200-600 triangles, slivers to cube-spanning, all surface kinds): the reference-algorithm octree, brute force
+    (build_trivial_bounding_box) and the oracle BVH agree on ids, t and colours, bounces and multi-sampling included."""
+    from test_gpu_parity import _random_scene
+    rng = np.random.RandomState(1000 + seed)
+    tris = _random_scene(R, rng, [200, 600][seed % 2])          # every triangle inside the root cube
+    ov = O.create_viewport((161, 121), (1.0, 121 / 161), [1.0, 0.5, -1.0], O.unit([0.1, -0.05, 1.0]), 90.0, 0.2, 6, 2)
+    a = O.Scene(tris.view(O.TRI_DTYPE), O.ACCEL_OCTREE).render(ov, seed=seed)
+    assert (a[1] > 0).mean() > 0.3
+    for accel in (O.ACCEL_TRIVIAL, O.ACCEL_BVH):
+        b = O.Scene(tris.view(O.TRI_DTYPE), accel).render(ov, seed=seed)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+        assert a[3].rays == b[3].rays
+
+
+def test_octree_misses_only_hits_outside_the_root_cube(R, O):
+    """Where the reference's octree and a true closest-hit search part ways, quantified: triangles that STICK OUT of the
+    octree root cube are kept by the root cull (a corner is inside, raytrace.rs:795-805), but a hit on their outer part is
+    found by the octree only if the ray also crosses a cell that lists the triangle.  On a soup with such triangles the
+    octree and brute force (build_trivial_bounding_box = what the GPU path returns) disagree on a few rays in ten thousand —
+    and every disagreement is a brute-force hit whose point lies outside the cube; the octree never returns a closer hit, and
+    never differs on a hit inside the cube.  (main.rs's scene lies inside its cube: no such ray exists there.)"""
+    from test_gpu_parity import _random_scene
+    tris = _random_scene(R, np.random.RandomState(1003), 600, inside_root_cube=False).view(O.TRI_DTYPE)
+    octree, brute = O.Scene(tris, O.ACCEL_OCTREE), O.Scene(tris, O.ACCEL_TRIVIAL)
+    r2 = np.random.RandomState(7)
+    n, mismatches = 12000, 0
+    for _ in range(n):
+        o = np.array([r2.uniform(-6, 8), r2.uniform(-9, 9), r2.uniform(0.5, 30)], np.float32)
+        d = O.unit(r2.uniform(-1, 1, 3))
+        a, b = octree.closest_hit(o, d), brute.closest_hit(o, d)
+        if a[0] == b[0]:
+            continue
+        mismatches += 1
+        assert b[0] != 0 and (a[0] == 0 or a[1] > b[1]), "the octree found a closer hit than brute force"
+        hp = o + d * np.float32(b[1])
+        assert not (abs(hp[0]) <= 20 and abs(hp[1]) <= 20 and 0.1 <= hp[2] <= 40.1), "a missed hit INSIDE the root cube"
+    assert 0 < mismatches < n // 500
