@@ -115,12 +115,12 @@ typedef struct RtbStats {
     uint64_t rays;            /* project_ray calls with depth>0 — the reference's "Rays" (raytrace.rs:1278) */
     uint64_t node_tests;      /* AABB slab tests   (RTB_FLAG_STATS only) */
     uint64_t tri_tests;       /* exact triangle tests (RTB_FLAG_STATS only) */
-    double   ms_render;       /* device time of the trace kernels, max over GPUs (CUDA events) */
+    double   ms_render;       /* device time of the frame's kernels, max over GPUs (CUDA events) */
     double   ms_total;        /* host wall time of the call incl. copies */
     uint32_t kernel_launches; /* kernels launched by this call */
     uint32_t n_gpus;
-    uint64_t bounce_rays;        /* rays traced by the bounce kernel (rays - primary rays)                */
-    uint64_t node_tests_bounce;  /* the share of node_tests / tri_tests spent in the bounce kernel        */
+    uint64_t bounce_rays;        /* rays after the primary ones (rays - primary rays): the bounce phase     */
+    uint64_t node_tests_bounce;  /* the share of node_tests / tri_tests spent on bounce rays               */
     uint64_t tri_tests_bounce;   /*   (RTB_FLAG_STATS only)                                               */
     double   ms_stage[4];        /* RTB_FLAG_TIMING: device ms per stage, summed over samples (CUDA events) */
     double   ms_reduce;          /* rtb_render_progressive: device ms of the cross-GPU reduce + copy home, max over GPUs */

@@ -105,12 +105,12 @@ struct TraceCounters {
     unsigned long long rays;
     unsigned long long node_tests;
     unsigned long long tri_tests;
-    unsigned long long node_tests_bounce;   // share of the two above spent in k_wf_bounce
+    unsigned long long node_tests_bounce;   // share of the two above spent on bounce rays (incl. their shadow rays)
     unsigned long long tri_tests_bounce;
     unsigned long long stalled;             // fused path kernel: watchdog trips (0 unless something is badly wrong)
 };
 
-// One compute lane of a GPU: a stream with its own wavefront workspace (ray queues, hit records, mix stacks, RNG).
+// One compute lane of a GPU: a stream with its own path workspace (bounce queue, mix stacks, sample sums).
 struct GpuLane {
     cudaStream_t st = nullptr;     // lane 0 runs on the caller's stream and leaves this null
     cudaEvent_t done = nullptr;
