@@ -169,8 +169,11 @@ def test_fused_launch_equals_the_two_phase_launches(R, O, scenes, spp, maxdepth,
     b = gpu_render(R, s, vs, seed=23, stats=True)
     assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
     assert a[3].total_rays == b[3].total_rays
-    assert a[4].stats.node_tests == b[4].stats.node_tests and a[4].stats.tri_tests == b[4].stats.tri_tests
-    assert a[4].stats.node_tests_bounce == b[4].stats.node_tests_bounce
+    # the bounce rays do identical work in both; the primary rays of the two-launch renderer push their far children
+    # half-sorted (three compare-exchanges instead of five), so their box / triangle test counts differ a little
+    assert a[4].stats.node_tests_bounce == b[4].stats.node_tests_bounce and a[4].stats.tri_tests_bounce == b[4].stats.tri_tests_bounce
+    assert abs(a[4].stats.node_tests - b[4].stats.node_tests) <= 0.01 * b[4].stats.node_tests
+    assert abs(a[4].stats.tri_tests - b[4].stats.tri_tests) <= 0.01 * b[4].stats.tri_tests
     assert_bit_exact(b, bvh.render(O.main_viewport(*wh, maxdepth, spp), seed=23), f"fused {wh} spp={spp} maxdepth={maxdepth}")
 
 
