@@ -182,6 +182,17 @@ ViewDev make_view(const RtbView& v, uint32_t rank, uint32_t world, bool compact)
     const uint32_t tiles_y = (v.height + RTB_TILE_H - 1) / RTB_TILE_H;
     d.my_tile_rows = tiles_y > rank ? (tiles_y - rank + world - 1) / world : 0;
     d.compact = compact ? 1u : 0u;
+    // the per-frame constants of pixel_ray, the RNG seeding and the slot -> pixel map (host code is compiled without
+    // contraction or fast-math: the same IEEE division and products the device would do per ray)
+    const float inv_w = 1.0f / (float)v.width, inv_h = 1.0f / (float)v.height;
+    for (int k = 0; k < 3; ++k) { d.vu_delta[k] = v.vu[k] * inv_w; d.vv_delta[k] = v.vv[k] * inv_h; }
+    uint64_t z = v.seed + 0x9E3779B97F4A7C15ull;                          // splitmix64, as rtb_device.cuh
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    d.seed_mixed = z ^ (z >> 31);
+    const uint32_t tiles_x8 = (v.width + 7u) / 8u;
+    d.div_band = rtb_udiv_make(2u * tiles_x8);
+    d.div_tx8 = rtb_udiv_make(tiles_x8);
     return d;
 }
 

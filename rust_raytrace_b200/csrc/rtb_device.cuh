@@ -58,8 +58,9 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 struct Rng {
     uint64_t state;
-    __device__ __forceinline__ void seed(uint64_t seed, uint64_t pixel, uint32_t sample) {
-        uint64_t s = splitmix64(seed);
+    // seed_mixed = splitmix64(seed), done once per frame on the host (ViewDev::seed_mixed)
+    __device__ __forceinline__ void seed(uint64_t seed_mixed, uint64_t pixel, uint32_t sample) {
+        uint64_t s = seed_mixed;
         s = splitmix64(s ^ pixel);
         s = splitmix64(s ^ (uint64_t)sample);
         state = s;
@@ -85,8 +86,8 @@ __device__ __forceinline__ V3 random_vec(Rng& g) {   // raytrace.rs:188-192
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void gen_primary(const ViewDev& vw, uint32_t row, uint32_t col, float u_off, float v_off,
                                             V3* o, V3* d) {
-    const V3 vu_delta = vmul(mk(vw.vu[0], vw.vu[1], vw.vu[2]), __fdiv_rn(1.0f, (float)vw.width));
-    const V3 vv_delta = vmul(mk(vw.vv[0], vw.vv[1], vw.vv[2]), __fdiv_rn(1.0f, (float)vw.height));
+    const V3 vu_delta = mk(vw.vu_delta[0], vw.vu_delta[1], vw.vu_delta[2]);   // vu * (1/width), vv * (1/height): make_view
+    const V3 vv_delta = mk(vw.vv_delta[0], vw.vv_delta[1], vw.vv_delta[2]);
     const V3 vu_frac = vmul(vu_delta, __fadd_rn((float)col, u_off));   // px = (row, col): px_y = col
     const V3 vv_frac = vmul(vv_delta, __fadd_rn((float)row, v_off));
     *o = vadd(vadd(mk(vw.orig[0], vw.orig[1], vw.orig[2]), vu_frac), vv_frac);

@@ -78,6 +78,30 @@ struct SceneDev {
 #define RTB_TILE_W 16
 #define RTB_TILE_H 8
 
+// Unsigned division by a divisor known on the host (Granlund & Montgomery 1994, the round-up method): exact for every 32-bit
+// numerator.  q = (t + ((n - t) >> s1)) >> s2 with t = mulhi(m, n).
+struct RtbUdiv { uint32_t m, s1, s2; };
+static inline RtbUdiv rtb_udiv_make(uint32_t d) {
+    RtbUdiv r;
+    uint32_t l = 0;
+    while ((1ull << l) < (unsigned long long)d) ++l;                       // ceil(log2 d)
+    r.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1ull);
+    r.s1 = l < 1u ? l : 1u;
+    r.s2 = l > 0u ? l - 1u : 0u;
+    return r;
+}
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline uint32_t rtb_udiv(uint32_t n, RtbUdiv d) {
+#ifdef __CUDA_ARCH__
+    const uint32_t t = __umulhi(d.m, n);
+#else
+    const uint32_t t = (uint32_t)(((unsigned long long)d.m * n) >> 32);
+#endif
+    return (t + ((n - t) >> d.s1)) >> d.s2;
+}
+
 struct ViewDev {
     uint32_t width, height;
     float orig[3], cam[3], vu[3], vv[3];
@@ -91,6 +115,10 @@ struct ViewDev {
     uint32_t my_tile_rows;   // number of this rank's bands rendered by this launch ...
     uint32_t band_begin;     // ... starting at its band_begin-th band (chunked rendering; 0 = from the first)
     uint32_t compact;        // 1: output rows are packed (own bands only), 0: full-frame indexing
+    // derived once on the host (make_view), so that no ray pays for them:
+    float vu_delta[3], vv_delta[3];   // vu * (1/width), vv * (1/height) — pixel_ray :1379-1380, the same IEEE operations
+    uint64_t seed_mixed;              // splitmix64(seed), the first of the three mixing steps of Rng::seed
+    RtbUdiv div_band, div_tx8;        // division of a warp-tile index by the tiles of a band / of a band half (slot_to_pixel)
 };
 
 // EXTENSION (rtb_ext.cu): analytic spheres travel as pseudo-triangles tagged in `kind`; the light of the reference's

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const ViewDev 
 
         for (uint32_t smp = vw.s_begin; smp < vw.s_end; ++smp) {
             Rng g;
-            g.seed(vw.seed, pix, smp);
+            g.seed(vw.seed_mixed, pix, smp);
             float u_off = 0.5f, v_off = 0.5f;
             if (vw.spp != 1) { u_off = g.next_f32(); v_off = g.next_f32(); }
             V3 o, d;
