@@ -201,6 +201,67 @@ static Bvh2 build_ploc(int R, bool sah_collapse) {
     return t;
 }
 
+
+// ---------------- insertion-based optimisation (Bittner et al. 2013; the one-subtree form of Meister & Bittner 2018) ----------------
+// Every node N (with its whole subtree) is taken out of the tree — its parent P disappears, its sibling takes P's place — and put
+// back as the sibling of the node X for which the sum of the inner nodes' surface areas grows least (branch and bound from the
+// root); the move is kept when the tree's summed area shrinks.  Leaves keep their primitives.
+static void reinsertion_opt(Bvh2& t, int passes) {
+    int N = (int)t.n.size();
+    std::vector<int> parent(N, -1);
+    for (int i = 0; i < N; ++i) if (t.n[i].l >= 0) { parent[t.n[i].l] = i; parent[t.n[i].r] = i; }
+    auto uni = [](const Box& a, const Box& b) { Box c = a; c.grow(b); return c; };
+    auto refit_up = [&](int v) { while (v >= 0) { t.n[v].box = uni(t.n[t.n[v].l].box, t.n[t.n[v].r].box); v = parent[v]; } };
+    auto total = [&]() { double c = 0; for (int i = 0; i < N; ++i) if (t.n[i].l >= 0 && (parent[i] >= 0 || i == t.root)) c += t.n[i].box.area(); return c; };
+    std::mt19937 rng(7);
+    for (int pass = 0; pass < passes; ++pass) {
+        double before = total();
+        std::vector<int> cand; for (int i = 0; i < N; ++i) if (i != t.root && parent[i] >= 0 && parent[i] != t.root) cand.push_back(i);
+        std::sort(cand.begin(), cand.end(), [&](int a, int b) { return t.n[parent[a]].box.area() > t.n[parent[b]].box.area(); });
+        int moved = 0;
+        for (int n : cand) {
+            int P = parent[n]; if (P < 0 || P == t.root) continue;
+            int G = parent[P]; int S = t.n[P].l == n ? t.n[P].r : t.n[P].l;
+            // cost of the inner nodes on the path before
+            double path_before = t.n[P].box.area(); for (int a = G; a >= 0; a = parent[a]) path_before += t.n[a].box.area();
+            // remove
+            if (t.n[G].l == P) t.n[G].l = S; else t.n[G].r = S; parent[S] = G;
+            std::vector<std::pair<int, Box>> saved; for (int a = G; a >= 0; a = parent[a]) saved.push_back({a, t.n[a].box});
+            refit_up(G);
+            double path_after = 0; for (int a = G; a >= 0; a = parent[a]) path_after += t.n[a].box.area();
+            double gain = path_before - path_after;
+            // best position: branch and bound on the induced cost
+            const Box nb = t.n[n].box; float na = nb.area();
+            double best = 1e300; int bx = -1;
+            std::vector<std::pair<double, int>> pq; pq.push_back({0.0, t.root});
+            auto cmp = [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; };
+            while (!pq.empty()) {
+                std::pop_heap(pq.begin(), pq.end(), cmp); auto [ind, x] = pq.back(); pq.pop_back();
+                if (ind + na >= best) break;
+                double direct = uni(t.n[x].box, nb).area();
+                if (ind + direct < best) { best = ind + direct; bx = x; }
+                if (t.n[x].l >= 0) {
+                    double ci = ind + direct - t.n[x].box.area();
+                    if (ci + na < best) { pq.push_back({ci, t.n[x].l}); std::push_heap(pq.begin(), pq.end(), cmp); pq.push_back({ci, t.n[x].r}); std::push_heap(pq.begin(), pq.end(), cmp); }
+                }
+            }
+            if (bx >= 0 && best < gain * (1.0 - 1e-6) && bx != S) {
+                int XP = parent[bx];
+                t.n[P].l = bx; t.n[P].r = n; parent[P] = XP; parent[bx] = P; parent[n] = P;
+                if (XP < 0) t.root = P; else { if (t.n[XP].l == bx) t.n[XP].l = P; else t.n[XP].r = P; }
+                refit_up(P); ++moved;
+            } else {   // put it back
+                for (auto& sv : saved) t.n[sv.first].box = sv.second;
+                if (t.n[G].l == S) t.n[G].l = P; else t.n[G].r = P; parent[P] = G; parent[S] = P;
+                t.n[P].l = S; t.n[P].r = n;
+            }
+        }
+        double after = total();
+        printf("  reinsertion pass %d: moved %d, inner area %.1f -> %.1f (%.2f %%)\n", pass, moved, before, after, 100.0 * (after - before) / before);
+        if (moved == 0 || (before - after) < 1e-4 * before) break;
+    }
+}
+
 // ---------------- BVH4 collapse + traversal ----------------
 struct N4 { Box b[4]; int code[4]; /* 0 empty, <0 leaf: -(idx2+1), >0: n4 index */ };
 struct Bvh4 { std::vector<N4> n; const Bvh2* src; };
@@ -354,6 +415,8 @@ int main(int argc, char** argv) {
 
     cfgs.push_back({"PLOC r=16 + SAH leaf split", build_ploc(16, true)});
     cfgs.push_back({"binned SAH top-down", build_sah()});
+    { Bvh2 o = build_sah(); reinsertion_opt(o, 8); cfgs.push_back({"binned SAH + reinsertion", o}); }
+    { Bvh2 o = build_ploc(16, true); reinsertion_opt(o, 8); cfgs.push_back({"PLOC + SAH leaf + reinsertion", o}); }
     // camera of main.rs at 4K, every 6th pixel
     V orig{2.28125f, -0.5f, 0.f}, cam{2.f, 0.f, -0.5f}, vu{0, 1, 0}, vv{-0.5625f, 0, 0};
     int W = 3840, H = 2160;
