@@ -84,7 +84,13 @@ def profiled_dram_traffic(name, world):
     configuration.  Returns (bytes, source file)."""
     if name != "teapot4k" or world != 1:
         return None, None
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_wf_path_bounce_raw.csv")), key=os.path.getmtime)
+    # the newest capture: profiles/CURRENT names its tag (file times do not survive the snapshot that travels to the GPU box)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_wf_path_bounce_raw.csv")))
+    cur = os.path.join(ROOT, "profiles", "CURRENT")
+    if os.path.exists(cur):
+        tagged = os.path.join(ROOT, "profiles", open(cur).read().strip() + "_k_wf_path_bounce_raw.csv")
+        if os.path.exists(tagged):
+            files = [tagged]
     if not files:
         return None, None
     tot, seen = 0.0, 0

@@ -29,6 +29,11 @@ __device__ __forceinline__ float vdot(V3 a, V3 b) {
     s = __fadd_rn(s, __fmul_rn(a.z, b.z));
     return __fadd_rn(s, 0.0f);
 }
+// the same dot for a value that is only COMPARED (x > y): the final "+ 0*0" can only turn -0 into +0, which no comparison sees
+__device__ __forceinline__ float vdot_cmp(V3 a, V3 b) {
+    float s = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+    return __fadd_rn(s, __fmul_rn(a.z, b.z));
+}
 __device__ __forceinline__ V3 vunit(V3 a) {   // :93-96: v * (1/len)
     float inv = __fdiv_rn(1.0f, __fsqrt_rn(vdot(a, a)));
     return vmul(a, inv);
@@ -106,13 +111,13 @@ __device__ __forceinline__ bool tri_test_pre(const float4* __restrict__ q, float
     if (t < 0.0f) return false;
     if (has && t > best) return false;
     const V3 ip = vsub(vadd(vmul(d, t), o), c);
-    if (vdot(ip, ip) > q0.w) return false;
+    if (vdot_cmp(ip, ip) > q0.w) return false;
     // the three edge records together: one latency instead of up to three (ncu r1_v5: these dependent loads held
     // 11 % of the bounce kernel's stall samples at ~4 active lanes)
     const float4 q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
-    if (vdot(ip, mk(q2.x, q2.y, q2.z)) > q2.w) return false;
-    if (vdot(ip, mk(q3.x, q3.y, q3.z)) > q3.w) return false;
-    if (vdot(ip, mk(q4.x, q4.y, q4.z)) > q4.w) return false;
+    if (vdot_cmp(ip, mk(q2.x, q2.y, q2.z)) > q2.w) return false;
+    if (vdot_cmp(ip, mk(q3.x, q3.y, q3.z)) > q3.w) return false;
+    if (vdot_cmp(ip, mk(q4.x, q4.y, q4.z)) > q4.w) return false;
     *t_out = t;
     return true;
 }
@@ -144,7 +149,7 @@ __device__ __forceinline__ int shade_hit(const SceneDev& sc, int slot, float t, 
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float4 qs = __ldg(q + 2 + i);
-        const float dist = vdot(ip, mk(qs.x, qs.y, qs.z));
+        const float dist = vdot_cmp(ip, mk(qs.x, qs.y, qs.z));
         if (dist > __fmul_rn(qs.w, edge_k)) hit_edge = true;
     }
     if (hit_edge) { *color = mk(0.0f, 0.0f, 0.0f); return 0; }
@@ -152,7 +157,7 @@ __device__ __forceinline__ int shade_hit(const SceneDev& sc, int slot, float t, 
     *color = mk(s0.x, s0.y, s0.z);
     if (kind == RTB_SOLID) return 0;
     *alpha = s0.w;
-    const bool back = vdot(d, n) > 0.0f;                     // :425-435
+    const bool back = vdot_cmp(d, n) > 0.0f;                 // :425-435
     const V3 nn = back ? vmul(n, -1.0f) : n;
     if (kind == RTB_MATTE) {                                 // lambertian_ray :292-297
         const V3 rv = random_vec(g);
