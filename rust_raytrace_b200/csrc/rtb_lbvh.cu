@@ -916,7 +916,8 @@ __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const in
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_internal > 0 ? n_internal : 1)) return;
     if (n_internal > 0 && !flags4[i]) return;
-    const float pad = o2f(s->max_abs) * (1.0f / 131072.0f);
+    // (centre, half extent) boxes: the slab test rounds three times per plane instead of twice, so the pad is doubled
+    const float pad = o2f(s->max_abs) * (RTB_NODE_CE ? 1.0f / 65536.0f : 1.0f / 131072.0f);
     auto leaf_final = [&](int c) { return kind[c] == KIND_LEAF; };
     int ent[4];
     int n_ent = 0;
@@ -942,6 +943,14 @@ __global__ void k_emit_nodes4(int n, const int2* __restrict__ children, const in
             const float4 l = blo[c], h = bhi[c];
             lo[0][e] = l.x - pad; lo[1][e] = l.y - pad; lo[2][e] = l.z - pad;
             hi[0][e] = h.x + pad; hi[1][e] = h.y + pad; hi[2][e] = h.z + pad;
+#if RTB_NODE_CE
+            // lo[] holds the centre, hi[] the half extent, rounded up so that [c - e, c + e] contains the padded box
+            for (int a = 0; a < 3; ++a) {
+                const float c0 = 0.5f * (lo[a][e] + hi[a][e]);
+                const float e0 = fmaxf(__fsub_ru(hi[a][e], c0), __fsub_ru(c0, lo[a][e]));
+                lo[a][e] = c0; hi[a][e] = e0;
+            }
+#endif
             if (leaf_final(c)) {
                 const uint32_t first = c >= n - 1 ? (uint32_t)(c - (n - 1)) : (uint32_t)range[c].x;
                 const uint32_t cnt = c >= n - 1 ? 1u : (uint32_t)(range[c].y - range[c].x + 1);
