@@ -266,6 +266,12 @@ int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t*
  * scans against the host on n pseudo-random pairs with key_bits significant key bits. */
 int rtb_selftest_sort(uint32_t n, int key_bits, uint64_t seed);
 
+/* Host self-test of the division by a per-frame constant that maps a pixel slot to its pixel (slot_to_pixel; Granlund &
+ * Montgomery's round-up method): q = n / d through the precomputed multiplier must equal the machine's n / d for divisor d and
+ * `samples` pseudo-random 32-bit numerators plus the boundary cases.  Returns the number of mismatches (0 = exact), or
+ * RTB_ERR_INVALID for d == 0.  Host-only; needs no GPU. */
+int rtb_selftest_udiv(uint32_t d, uint32_t samples, uint64_t seed);
+
 /* ---- one process per GPU, one frame on one GPU (torchrun; reference: the row queue all workers write one `data` slice
  * from, raytrace.rs:1179-1194) ------------------------------------------------------------------------------------
  * The root rank allocates the frame with rtb_device_alloc and exports it (rtb_ipc_export, a 64-byte

@@ -114,7 +114,7 @@ RTB_SYMBOLS = [
     "rtb_init", "rtb_device_count", "rtb_visible_device_count", "rtb_shutdown", "rtb_last_error", "rtb_scene_create", "rtb_scene_info",
     "rtb_scene_destroy", "rtb_scene_download_bvh", "rtb_render_rgb8", "rtb_scene_create_instanced", "rtb_assemble_triangles",
     "rtb_cull_triangles", "rtb_scene_create_ext", "rtb_scene_set_light", "rtb_render", "rtb_render_device", "rtb_render_progressive",
-    "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
+    "rtb_quantize_rgb8", "rtb_scale_device", "rtb_selftest_sort", "rtb_selftest_udiv", "rtb_partition_rows", "rtb_host_register", "rtb_host_unregister",
     "rtb_device_alloc", "rtb_device_free", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close",
 ]
 RTBH_SYMBOLS = [
@@ -168,6 +168,7 @@ def lib():
     L.rtb_quantize_rgb8.argtypes = [vp, C.c_uint64, vp]
     L.rtb_scale_device.argtypes = [vp, C.c_uint64, u32, C.c_int, vp]
     L.rtb_selftest_sort.argtypes = [u32, C.c_int, C.c_uint64]
+    L.rtb_selftest_udiv.argtypes = [u32, u32, C.c_uint64]
     L.rtb_partition_rows.argtypes = [u32, u32, u32, vp, u32]
     L.rtb_host_register.argtypes = [vp, C.c_size_t]
     L.rtb_host_unregister.argtypes = [vp]

@@ -1085,6 +1085,22 @@ int rtb_selftest_sort(uint32_t n, int key_bits, uint64_t seed) {
     return rtb_sort_selftest(n, key_bits, seed);
 }
 
+int rtb_selftest_udiv(uint32_t d, uint32_t samples, uint64_t seed) {
+    if (d == 0) return fail(RTB_ERR_INVALID, "division by zero");
+    const RtbUdiv m = rtb_udiv_make(d);
+    int bad = 0;
+    const uint32_t edge[] = {0u, 1u, d - 1u, d, d + 1u, 2u * d - 1u, 2u * d, 0x7fffffffu, 0x80000000u, 0xfffffffeu, 0xffffffffu,
+                             0xffffffffu / d * d, 0xffffffffu / d * d - 1u};
+    for (uint32_t n : edge) bad += rtb_udiv(n, m) != n / d;
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+    for (uint32_t k = 0; k < samples; ++k) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;                         // xorshift64
+        const uint32_t n = (uint32_t)(x >> 16);
+        bad += rtb_udiv(n, m) != n / d;
+    }
+    return bad;
+}
+
 int rtb_partition_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t* rows_out, uint32_t cap) {
     if (world == 0 || rank >= world) return fail(RTB_ERR_INVALID, "bad rank/world");
     uint32_t n = 0;

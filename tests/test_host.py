@@ -171,6 +171,19 @@ def test_band_partition_covers_every_row_once(R):
     assert L.rtb_partition_rows(10, 3, 2, None, 0) < 0
 
 
+def test_slot_to_pixel_division_is_exact(R):
+    """slot_to_pixel divides a warp-tile index by the tiles of a band with a multiplier computed once per frame on the host
+    (rtb_udiv_make / rtb_udiv, Granlund & Montgomery): it must equal the machine's division for every divisor an image width
+    can produce (1 .. 2 * ceil(65536 / 8)) and for awkward ones, over the whole 32-bit range of numerators."""
+    from rust_raytrace_b200 import _lib
+    L = _lib.lib()
+    divisors = list(range(1, 1200)) + [2 * ((w + 7) // 8) for w in (3840, 7680, 2560, 1283, 65535)] + \
+        [2**k for k in range(1, 32)] + [2**k - 1 for k in range(2, 32)] + [2**k + 1 for k in range(1, 31)] + [0xffffffff, 0x80000001]
+    for d in divisors:
+        assert L.rtb_selftest_udiv(d, 400, d) == 0, d
+    assert L.rtb_selftest_udiv(0, 1, 0) == _lib.RTB_ERR_INVALID
+
+
 def test_gpu_path_fails_loudly_without_a_device(R):
     """No CPU fallback: on a machine without CUDA the render call must raise, not produce pixels."""
     import torch
