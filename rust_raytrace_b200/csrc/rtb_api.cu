@@ -149,7 +149,7 @@ int check_view(const RtbView* v) {
 }
 
 // The conservative slab tests compute t = fma(plane, 1/d, -o/d): the rounding of o/d moves a plane by up to |o| * 2^-23,
-// which the builder's padding (2^-17 of the scene's largest |coordinate|) covers only while the ray origins stay within
+// which the builder's padding (2^-16 of the scene's largest |coordinate| for the BVH4, 2^-17 for the BVH2) covers only while the ray origins stay within
 // 32x the scene's extent.  Bounce rays start on surfaces; primary rays start on the viewport plane — checked here.
 int check_camera(const rtb_scene* s, const RtbView* v) {
     float max_abs = 0.f;

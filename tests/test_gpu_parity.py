@@ -229,6 +229,30 @@ def test_rotated_camera(R, O, scenes):
     assert_bit_exact(gpu_render(R, s, rv), bvh.render(ov), "rotated camera")
 
 
+def test_far_camera_near_the_range_limit(R, O, scenes):
+    """The conservative slab test of the BVH4 traversal (centre / half-extent boxes, three FMA roundings per plane) is
+    covered by the builder's box padding only while the viewport stays within 32x the scene's largest coordinate
+    (rtb_api.cu check_camera).  Close to that limit — a viewport 260 units away from a scene whose largest coordinate is
+    8.6 (the limit is 276), looking at the teapot through a 1 degree lens — the traversal must still return exactly what the linear scan over every
+    primitive (RTB_FLAG_BRUTE) and the CPU oracle return; one step beyond the limit the call is refused."""
+    from rust_raytrace_b200 import _lib
+    s, _, bvh = scenes[True]
+    args = ((400, 300), (1.0, 0.75), [2.0, 0.0, -260.0], None, 1.0, 0.0, 5, 1)
+    rv = R.create_viewport(*args[:3], R.unit([0.0, 0.0, 1.0]), *args[4:])
+    ov = O.create_viewport(*args[:3], O.unit([0.0, 0.0, 1.0]), *args[4:])
+    a = gpu_render(R, s, rv, seed=5)
+    assert (a[1] != 0).mean() > 0.15                                  # the teapot and the disks are in view
+    vb = _lib.RtbView.from_buffer_copy(rv)
+    vb.flags |= _lib.RTB_FLAG_BRUTE
+    b = gpu_render(R, s, vb, seed=5)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[0]), bits(b[0]))
+    assert a[3].total_rays == b[3].total_rays
+    assert_bit_exact(a, bvh.render(ov, seed=5), "far camera")
+    too_far = R.create_viewport(args[0], args[1], [2.0, 0.0, -400.0], R.unit([0.0, 0.0, 1.0]), *args[4:])
+    with pytest.raises(Exception):
+        gpu_render(R, s, too_far)
+
+
 def test_empty_and_tiny_scenes(R, O):
     v, ov = R.main_viewport(64, 48, 5, 1), O.main_viewport(64, 48, 5, 1)
     only_dummy = R.Scene(R.make_dummy_triangle())
