@@ -817,7 +817,8 @@ __global__ void k_emit_nodes(int n, const int2* __restrict__ children, const int
 // A BVH4 node is rooted at the root and at every internal node that covers more than RTB_LEAF_MAX primitives
 // and sits at EVEN depth of the binary tree; its (up to 4) entries are its grandchildren, or a child
 // itself where that child is already a leaf.  Node = 8 x float4 (128 B, one cache line), SoA over the
-// entries: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] code[4] pad.  code: 0 = empty slot,
+// entries: c.x[4] e.x[4] c.y[4] e.y[4] c.z[4] e.z[4] code[4] pad — child boxes as centre and half extent (RTB_NODE_CE, rtb_internal.cuh;
+// lo / hi planes with RTB_NODE_CE=0), an empty slot's box all NaN.  code: 0 = empty slot,
 // 0x80000000 | first<<3 | count = leaf, otherwise the index of the child BVH4 node.
 __global__ void k_flag4(int n_internal, const uint8_t* __restrict__ kind, const int* __restrict__ parent,
                         uint32_t* __restrict__ flags4, BuildScratch* s) {
